@@ -1,0 +1,400 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI,
+against the CPU oracle and the golden fixtures captured from the reference.
+
+Bars (BASELINE.json north_star): integer work (labels for identical logits, confusion matrices)
+bit-exact; low-res logits within 1e-5 of max|logit| (fp32-grade paths) or 2e-2 (bf16); label
+agreement with the reference path >= 99.99 % with disagreements only at fp ties; mIoU within 1e-4.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["int8x", "nonint", "x16", "same", "down", "wideq", "ties", "nan"]
+
+
+@pytest.fixture(scope="module")
+def zb(cuda_device):
+    import zutis_b200
+    from zutis_b200 import _ffi, ops
+    _ffi.check(_ffi.lib().zutis_device_check(0))
+    return zutis_b200
+
+
+def dev(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def pixel_major(logits_bqhw: torch.Tensor) -> torch.Tensor:
+    """[B,Q,h,w] view over [B,h,w,Qp] memory (what the contraction kernel emits)."""
+    B, Q, h, w = logits_bqhw.shape
+    Qp = (Q + 3) & ~3
+    buf = torch.zeros(B, h, w, Qp, device=logits_bqhw.device)
+    buf[..., :Q] = logits_bqhw.permute(0, 2, 3, 1)
+    return buf[..., :Q].permute(0, 3, 1, 2)
+
+
+def tie_gap_ok(full_ref: np.ndarray, a: np.ndarray, b: np.ndarray, ulps: float = 16.0) -> bool:
+    """Every pixel where label maps a and b differ must be a near-tie of the reference's full-res logits."""
+    bad = np.argwhere(a != b)
+    scale = np.abs(full_ref).max() * np.finfo(np.float32).eps
+    for (bi, y, x) in bad:
+        col = full_ref[bi, :, y, x]
+        if abs(float(col[a[bi, y, x]]) - float(col[b[bi, y, x]])) > ulps * scale:
+            return False
+    return True
+
+
+# ------------------------------------------------------------------------------ contraction
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("auto", 1e-5)])
+def test_contraction_model_cfg1(zb, golden, precision, tol):
+    g = golden("model_cfg1")
+    out = zb.ops.contraction(dev(g["text"]), dev(g["tokens"]), precision=precision)
+    torch.cuda.synchronize()
+    ref = g["lowres_logits"]
+    assert tuple(out.shape) == ref.shape and out.stride(1) == 1          # pixel-major memory
+    assert np.abs(out.cpu().numpy() - ref).max() / np.abs(ref).max() <= tol
+    out2 = zb.ops.contraction(dev(g["text"]), dev(g["tokens"]), precision=precision, pixel_major=False)
+    assert out2.is_contiguous() and torch.equal(out2, out.contiguous())
+
+
+@pytest.mark.parametrize("name", ["int8x", "nonint", "x16", "wideq"])
+def test_contraction_small_k_cases(zb, golden, name):
+    g = golden("decode_cases")
+    out = zb.ops.contraction(dev(g[f"{name}_text"]), dev(g[f"{name}_tokens"]))      # K = 32/16/24: SIMT or tcgen05
+    ref = g[f"{name}_lowres"]
+    assert np.abs(out.cpu().numpy() - ref).max() / np.abs(ref).max() <= 1e-5
+
+
+def test_contraction_batched_queries_with_sigmoid(zb):
+    gen = torch.Generator().manual_seed(3)
+    q3 = torch.randn(2, 10, 96, generator=gen); q3 = q3 / q3.norm(dim=-1, keepdim=True)
+    q4 = torch.randn(2, 3, 10, 96, generator=gen); q4 = q4 / q4.norm(dim=-1, keepdim=True)
+    feats = torch.randn(2, 5, 7, 96, generator=gen)
+    dec = zb.ZutisDecoder(torch.zeros(2, 96).cuda())
+    for q in (q3, q4):
+        ref = O.torch_mask_proposals(q, feats).numpy()
+        got = dec.get_mask_proposals(q.cuda(), feats.cuda(), return_binary_masks=False)
+        assert tuple(got.shape) == ref.shape
+        np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=0, atol=2e-6)
+    raw, one_hot = dec.get_mask_proposals(q3.cuda(), feats.cuda(), return_binary_masks=True)
+    ref_raw = torch.einsum("bqc,bhwc->bqhw", q3, feats)
+    np.testing.assert_allclose(raw.cpu().numpy(), ref_raw.numpy(), atol=2e-6)
+    assert one_hot.dtype == torch.bool and tuple(one_hot.shape) == (2, 10, 5, 7)
+    assert torch.equal(one_hot.long().argmax(1).cpu(), raw.cpu().argmax(1))
+    assert int(one_hot.sum()) == 2 * 5 * 7
+
+
+# ------------------------------------------------------------------- fused decode, fixed logits
+@pytest.mark.parametrize("layout", ["bqhw", "pixel_major"])
+@pytest.mark.parametrize("name", CASES)
+def test_decode_labels_bit_exact_vs_c_oracle(zb, golden, name, layout):
+    from zutis_b200 import _ffi
+    g = golden("decode_cases")
+    H, W = (int(v) for v in g[f"{name}_size"])
+    lo = g[f"{name}_lowres"]
+    want = O.c_decode_semantic(lo, (H, W))
+    t = dev(lo)
+    if layout == "pixel_major":
+        t = pixel_major(t)
+    modes = [_ffi.DECODE_AUTO, _ffi.DECODE_GENERIC]
+    for mode in modes:
+        labels = zb.ops.decode_score(t, (H, W), mode=mode)
+        assert labels.dtype == torch.int16
+        assert np.array_equal(labels.cpu().numpy().astype(np.int64), want), f"mode {mode}"
+    # the golden labels come from ATen itself; identical except (possibly) at fp ties for tiny outputs
+    ref = g[f"{name}_labels"].astype(np.int64)
+    if max(H, W) > 64 or name in ("ties", "nan"):
+        assert np.array_equal(want, ref)
+    else:
+        assert (want == ref).mean() >= 0.999
+
+
+def test_decode_size_none_is_plain_argmax(zb, golden):
+    g = golden("model_cfg1")
+    labels = zb.ops.decode_score(dev(g["lowres_logits"]), None)
+    assert np.array_equal(labels.cpu().numpy(), g["labels_lowres"])
+
+
+def test_tiled_kernel_is_selected_and_equals_generic(zb):
+    """The two kernels are independent implementations; they must agree bit for bit."""
+    from zutis_b200 import _ffi
+    gen = torch.Generator().manual_seed(11)
+    for (B, Q, h, w, H, W) in [(3, 81, 20, 20, 160, 160), (2, 81, 13, 17, 107, 139), (1, 130, 9, 9, 150, 150),
+                               (2, 7, 6, 8, 96, 128), (1, 81, 14, 14, 224, 224)]:
+        lo = torch.randn(B, Q, h, w, generator=gen).cuda()
+        for t in (lo, pixel_major(lo)):
+            a = zb.ops.decode_score(t, (H, W), mode=_ffi.DECODE_TILED)
+            b = zb.ops.decode_score(t, (H, W), mode=_ffi.DECODE_GENERIC)
+            assert torch.equal(a, b)
+        want = O.c_decode_semantic(lo.cpu().numpy(), (H, W))
+        assert np.array_equal(a.cpu().numpy().astype(np.int64), want)
+    with pytest.raises(zb.ZutisUnsupported):
+        zb.ops.decode_score(torch.randn(1, 5, 30, 30).cuda(), (40, 40), mode=_ffi.DECODE_TILED)   # scale too small
+
+
+def test_nan_and_inf_follow_torch_argmax(zb):
+    from zutis_b200 import _ffi
+    gen = torch.Generator().manual_seed(5)
+    lo = torch.randn(2, 9, 6, 6, generator=gen)
+    lo[0, 3, 2, 2] = float("nan"); lo[0, 5, 2, 3] = float("nan"); lo[1, 4, 0, 0] = float("inf"); lo[1, 2, 5, 5] = float("-inf")
+    want = torch.argmax(torch.nn.functional.interpolate(lo, size=(96, 96), mode="bilinear"), dim=1).numpy()
+    want_c = O.c_decode_semantic(lo.numpy(), (96, 96))
+    assert np.array_equal(want, want_c)
+    for mode in (_ffi.DECODE_GENERIC, _ffi.DECODE_TILED, _ffi.DECODE_AUTO):
+        got = zb.ops.decode_score(lo.cuda(), (96, 96), mode=mode).cpu().numpy()
+        assert np.array_equal(got, want), f"mode {mode}"
+    wide = torch.randn(1, 200, 5, 5, generator=gen); wide[0, 150, 1, 1] = float("nan")       # NaN in a later chunk
+    want = O.c_decode_semantic(wide.numpy(), (80, 80))
+    assert np.array_equal(zb.ops.decode_score(wide.cuda(), (80, 80), mode=_ffi.DECODE_TILED).cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("gt_dtype", [torch.uint8, torch.int16, torch.int32, torch.int64])
+def test_fused_histogram_bit_exact(zb, gt_dtype):
+    from zutis_b200 import _ffi
+    gen = torch.Generator().manual_seed(21)
+    B, Q, h, w, H, W = 3, 81, 12, 15, 96, 120
+    lo = torch.randn(B, Q, h, w, generator=gen)
+    gt = torch.randint(0, Q, (B, H, W), generator=gen)
+    gt[:, :5] = 255; gt[1, 40:50, 10:60] = 200
+    if gt_dtype != torch.uint8:
+        gt[2, 7] = -1
+        gt[0, 9, :30] = 1000
+    labels_ref = O.c_decode_semantic(lo.numpy(), (H, W))
+    gt_np = gt.to(gt_dtype).numpy().astype(np.int64)
+    want = O.c_fast_hist(gt_np, labels_ref, Q)
+    for mode in (_ffi.DECODE_TILED, _ffi.DECODE_GENERIC):
+        part = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
+        labels = zb.ops.decode_score(pixel_major(lo.cuda()), (H, W), gt=gt.to(gt_dtype).cuda(), hist_partial=part, mode=mode)
+        assert np.array_equal(labels.cpu().numpy(), labels_ref)
+        assert np.array_equal(part.view(Q, Q).cpu().numpy().astype(np.int64), want)
+        hist = torch.zeros(Q * Q, dtype=torch.int64, device="cuda")
+        zb.ops.hist_merge(part, hist, clear=True)
+        zb.ops.hist_merge(part, hist, clear=True)              # partial was cleared: second merge adds nothing
+        assert np.array_equal(hist.view(Q, Q).cpu().numpy(), want) and int(part.abs().sum()) == 0
+    # histogram without labels, wide class count (global-atomic path), all-ignored image
+    Qw = 300
+    low = torch.randn(2, Qw, 5, 6, generator=gen)
+    gtw = torch.randint(0, Qw, (2, 80, 96), generator=gen); gtw[1] = 1000
+    part = torch.zeros(Qw * Qw, dtype=torch.int32, device="cuda")
+    assert zb.ops.decode_score(low.cuda(), (80, 96), gt=gtw.cuda(), hist_partial=part, want_labels=False) is None
+    want = O.c_fast_hist(gtw.numpy(), O.c_decode_semantic(low.numpy(), (80, 96)), Qw)
+    assert np.array_equal(part.view(Qw, Qw).cpu().numpy().astype(np.int64), want)
+    assert want.sum() == 80 * 96
+
+
+# ------------------------------------------------------------------ drop-in predict + RunningScore
+def test_semantic_predict_drop_in_model_cfg1(zb, golden):
+    """ZUTIS.predict('semantic') + RunningScore on the reference's own random-init ViT-B/32 outputs."""
+    g = golden("model_cfg1")
+    dec = zb.ZutisDecoder(dev(g["text"]))
+    pred = dec.predict({"patch_tokens": dev(g["tokens"])}, "semantic", size=(224, 224))
+    assert isinstance(pred, np.ndarray) and pred.dtype == np.int64 and pred.shape == (2, 224, 224)
+    ref = g["labels"].astype(np.int64)
+    agree = (pred == ref).mean()
+    assert agree >= 0.9999, agree
+    full = O.torch_semantic_predict(torch.from_numpy(g["text"]), torch.from_numpy(g["tokens"]), (224, 224), return_logits=True).numpy()
+    assert tie_gap_ok(full, pred, ref)
+    # confusion matrix: bit-exact for the labels the kernel produced; scores within 1e-4 of the reference's
+    meter = zb.RunningScore(81)
+    meter.update(g["gt"].astype(np.int64), pred)                      # host numpy, like trainer.py:347
+    assert np.array_equal(meter.confusion_matrix, O.c_fast_hist(g["gt"], pred, 81).astype(np.float64))
+    s, cls = meter.get_scores()
+    ref_scores = g["scores"]
+    got = np.array([s["Pixel Acc"], s["Mean Acc"], s["FreqW Acc"], s["Mean IoU"]])
+    assert np.abs(got - ref_scores).max() <= 1e-4
+    if agree == 1.0:
+        assert np.array_equal(got, ref_scores) and np.array_equal(meter.confusion_matrix, g["confusion"].astype(np.float64))
+    # fused path gives the same matrix without host labels
+    fused = zb.RunningScore(81)
+    dec.decode_and_score(dev(g["tokens"]), dev(g["gt"]), (224, 224), fused)
+    assert np.array_equal(fused.confusion_matrix, meter.confusion_matrix)
+    # return_logits=True still returns full-resolution fp32 logits
+    logits = dec.predict({"patch_tokens": dev(g["tokens"])}, "semantic", size=(224, 224), return_logits=True)
+    assert tuple(logits.shape) == (2, 81, 224, 224) and logits.dtype == torch.float32
+    assert np.abs(logits.cpu().numpy() - full).max() <= 1e-5 * np.abs(full).max() + 1e-6
+    lowres_labels = dec.predict({"patch_tokens": dev(g["tokens"])}, "semantic")          # size=None
+    assert (lowres_labels == g["labels_lowres"]).mean() >= 0.99
+
+
+@pytest.mark.parametrize("name", ["int8x", "nonint", "x16", "down", "wideq", "ties"])
+def test_semantic_predict_drop_in_cases(zb, golden, name):
+    g = golden("decode_cases")
+    H, W = (int(v) for v in g[f"{name}_size"])
+    dec = zb.ZutisDecoder(dev(g[f"{name}_text"]))
+    size = (H, W) if name != "nonint" else [torch.tensor([H]), torch.tensor([W])]        # trainer.py:322-323 form
+    pred = dec.predict({"patch_tokens": dev(g[f"{name}_tokens"])}, "semantic", size=size)
+    ref = g[f"{name}_labels"].astype(np.int64)
+    full = O.torch_semantic_predict(torch.from_numpy(g[f"{name}_text"]), torch.from_numpy(g[f"{name}_tokens"]), (H, W),
+                                    return_logits=True).numpy()
+    if name == "ties":
+        # exact duplicates of a category: the first index must win everywhere (torch.argmax rule)
+        assert not np.isin(pred, [4, 5]).any() and np.array_equal(pred, ref)
+    else:
+        assert tie_gap_ok(full, pred, ref)
+        assert (pred == ref).mean() >= (0.9999 if pred.size >= 20000 else 0.995)
+
+
+def test_upsample_bilinear_bit_exact(zb, golden):
+    g = golden("decode_cases")
+    for name in ("int8x", "nonint", "x16", "same"):
+        H, W = (int(v) for v in g[f"{name}_size"])
+        out = zb.ops.upsample_bilinear(dev(g[f"{name}_lowres"][:, :4]), (H, W)).cpu().numpy()
+        assert np.array_equal(out.view(np.int32), g[f"{name}_full4"].view(np.int32))
+
+
+def test_running_score_drop_in(zb, golden):
+    g = golden("scoring")
+    for n in (3, 4):
+        m = zb.RunningScore(n)
+        m.update(g["ka_gt"][None], g["ka_pred"][None])
+        assert np.array_equal(m.confusion_matrix, g[f"ka{n}_confusion"]) and m.confusion_matrix.dtype == np.float64
+        s, c = m.get_scores()
+        assert np.array_equal(np.array([s["Pixel Acc"], s["Mean Acc"], s["FreqW Acc"], s["Mean IoU"]]), g[f"ka{n}_scores"])
+        assert np.array_equal(np.array([c[i] for i in range(n)]), g[f"ka{n}_class_iou"], equal_nan=True)
+        assert list(s) == ["Pixel Acc", "Mean Acc", "FreqW Acc", "Mean IoU"] and list(c) == list(range(n))
+    # wide matrix, two updates, ignore labels 1000 and negatives
+    gt, pr = g["wide_gt"].astype(np.int64), g["wide_pred"].astype(np.int64)
+    m = zb.RunningScore(920)
+    m.update(gt, pr); m.update(torch.from_numpy(gt[:1]).cuda(), torch.from_numpy(pr[:1]).cuda().to(torch.int16))
+    ref = np.zeros((920, 920)); r, c, v = g["wide_confusion_nz"]; ref[r.astype(int), c.astype(int)] = v
+    assert np.array_equal(m.confusion_matrix, ref)
+    s, cls = m.get_scores()
+    assert np.array_equal(np.array([s["Pixel Acc"], s["Mean Acc"], s["FreqW Acc"], s["Mean IoU"]]), g["wide_scores"])
+    assert np.array_equal(np.array([cls[i] for i in range(920)]), g["wide_class_iou"], equal_nan=True)
+    # ragged list of differently sized images
+    m = zb.RunningScore(7)
+    m.update([g["rag_ga"], g["rag_gb"]], [g["rag_pa"], g["rag_pb"]])
+    assert np.array_equal(m.confusion_matrix, g["rag_confusion"])
+    m.reset()
+    assert m.confusion_matrix.sum() == 0
+    s, _ = m.get_scores()                                    # empty matrix -> nan / nan / 0 / nan
+    assert np.isnan(s["Pixel Acc"]) and np.isnan(s["Mean Acc"]) and s["FreqW Acc"] == 0.0 and np.isnan(s["Mean IoU"])
+    # an all-ignored image changes nothing
+    m.update(np.full((1, 5, 5), 255), np.zeros((1, 5, 5), np.int64))
+    assert m.confusion_matrix.sum() == 0
+
+
+def test_compute_iou_drop_in(zb, golden):
+    g = golden("scoring")
+    a = np.array([[1, 1, 0], [0, 1, 0]], bool); b = np.array([[1, 0, 0], [0, 1, 1]], bool)
+    r = zb.compute_iou(a, b)
+    assert isinstance(r, np.floating) and r == float(g["iou_bool"]) == 0.4999999875000003
+    pf = np.array([[.6, .4, .9], [.1, .7, .2]])
+    assert zb.compute_iou(pf, b, threshold=0.5) == float(g["iou_thr"])
+    assert zb.compute_iou(np.zeros((2, 3), bool), np.zeros((2, 3), bool)) == 0.0
+    assert zb.compute_iou(g["iou_rand_a"], g["iou_rand_b"]) == float(g["iou_rand"])
+    t = zb.compute_iou(torch.from_numpy(a), torch.from_numpy(b))
+    assert isinstance(t, torch.Tensor) and t.dim() == 0 and not t.is_cuda
+    assert np.array_equal(t.numpy(), g["iou_torch"])
+    with pytest.raises(AssertionError):
+        zb.compute_iou(np.zeros((2, 3)), np.zeros((3, 2)))
+
+
+# --------------------------------------------------------------------------------- instance path
+def test_threshold_masks_bit_exact(zb):
+    gen = torch.Generator().manual_seed(4)
+    probs = torch.sigmoid(3 * torch.randn(2, 10, 6, 8, generator=gen))
+    for size in [(48, 64), (50, 70), None]:
+        want = O.c_decode_threshold(probs.numpy(), size, 0.5)
+        bits, areas = zb.ops.decode_threshold(probs.cuda(), size, 0.5)
+        W = want.shape[-1]
+        got = zb.ops.unpack_mask_bits(bits, W).cpu().numpy()
+        assert np.array_equal(got, want)
+        assert np.array_equal(areas.cpu().numpy(), want.sum((-2, -1)))
+        inter = zb.ops.pairwise_mask_intersections(bits[0]).cpu().numpy()
+        flat = want[0].reshape(10, -1).astype(np.int64)
+        assert np.array_equal(inter, flat @ flat.T)
+
+
+@pytest.mark.parametrize("fixture,prefix", [("instance_cases", ""), ("model_cfg1", "inst_")])
+@pytest.mark.parametrize("tag", ["hard", "none"])
+def test_instance_predict_drop_in(zb, golden, fixture, prefix, tag):
+    g = golden(fixture)
+    size = tuple(int(v) for v in g["size"]) if "size" in g else (224, 224)
+    ids = [5, 6] if fixture == "instance_cases" else [11, 22]
+    dec = zb.ZutisDecoder(dev(g["text"]))
+    preds = dec.predict({"mask_proposals": dev(g["proposals"]), "patch_tokens": dev(g["tokens"])}, "instance",
+                        size=size, image_ids=ids, nms_type="hard" if tag == "hard" else None)
+    assert [p["category_id"] for p in preds] == g[f"{prefix}{tag}_category"].tolist()
+    assert [p["image_id"] for p in preds] == g[f"{prefix}{tag}_image_id"].tolist()
+    np.testing.assert_allclose(np.array([p["score"] for p in preds], np.float64).reshape(-1), g[f"{prefix}{tag}_score"], rtol=5e-6, atol=1e-9)
+    ref_bits = g[f"{prefix}{tag}_mask_bits"]
+    H, W = size
+    for p, rb, box in zip(preds, ref_bits, g[f"{prefix}{tag}_bbox"]):
+        assert set(p) >= {"category_id", "segmentation", "score", "image_id", "image_size", "bbox"}
+        assert tuple(p["image_size"]) == (H, W)
+        mask = np.unpackbits(rb)[: H * W].reshape(H, W).astype(bool)
+        seg = p["segmentation"]
+        if isinstance(seg, dict) and isinstance(seg.get("counts"), list):            # uncompressed COCO RLE
+            flat = np.zeros(H * W, np.uint8); pos = 0; val = 0
+            for run in seg["counts"]:
+                flat[pos:pos + run] = val; pos += run; val ^= 1
+            assert np.array_equal(flat.reshape(W, H).T.astype(bool), mask)
+        assert p["bbox"] == list(box)
+
+
+# ----------------------------------------------------------------------------- host-buffer entry
+def test_semantic_eval_host_entry(zb, golden):
+    import ctypes as C
+    from zutis_b200 import _ffi
+    g = golden("model_cfg1")
+    text = np.ascontiguousarray(g["text"]); tokens = np.ascontiguousarray(g["tokens"])
+    gt = np.ascontiguousarray(g["gt"].astype(np.int64))
+    hist = np.zeros((81, 81), np.int64); labels = np.zeros((2, 224, 224), np.int16)
+    _ffi.call("zutis_semantic_eval_host", text.ctypes.data, tokens.ctypes.data, gt.ctypes.data, _ffi.GT_I64,
+              2, 81, 512, 14, 14, 224, 224, hist.ctypes.data, labels.ctypes.data, _ffi.GEMM_FP32_SIMT, 0)
+    assert (labels == g["labels"]).mean() >= 0.9999
+    assert np.array_equal(hist, O.c_fast_hist(gt, labels.astype(np.int64), 81))
+
+
+# ------------------------------------------------------- BASELINE-size runs: size-independent properties
+FULL = {
+    "cfg2": dict(B=64, Q=81, D=512, h=40, w=40, H=320, W=320, ignore=255),
+    "cfg3": dict(B=32, Q=81, D=512, h=64, w=64, H=512, W=512, ignore=255),
+    "cfg4": dict(B=32, Q=920, D=512, h=56, w=56, H=448, W=448, ignore=1000),
+}
+
+
+@pytest.mark.parametrize("cfg", list(FULL))
+def test_full_size_properties(zb, cfg):
+    """At BASELINE.json's sizes the oracle is too slow, so check what must hold regardless of size:
+    counts conserve pixels, rows reproduce the ground-truth class histogram, columns the label
+    histogram, the fused matrix equals scoring the emitted labels, and two kernels agree."""
+    from zutis_b200 import _ffi
+    c = FULL[cfg]
+    B, Q, D, h, w, H, W = (c[k] for k in ("B", "Q", "D", "h", "w", "H", "W"))
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    text = torch.nn.functional.normalize(torch.randn(Q, D, device="cuda", generator=gen), dim=-1)
+    coarse = torch.randn(B, D, h // 2, w // 2, device="cuda", generator=gen)
+    tokens = torch.nn.functional.normalize(torch.nn.functional.interpolate(coarse, scale_factor=2, mode="bilinear").permute(0, 2, 3, 1), dim=-1).contiguous()
+    gt = torch.randint(0, Q, (B, H, W), device="cuda", generator=gen)
+    gt[:, :9] = c["ignore"]; gt[0] = c["ignore"]
+    meter = zb.RunningScore(Q)
+    labels = zb.decode_and_score(text, tokens, gt, (H, W), meter, want_labels=True)
+    counts = meter.counts()
+    valid = (gt >= 0) & (gt < Q)
+    assert int(counts.sum()) == int(valid.sum())
+    assert torch.equal(counts.sum(1), torch.bincount(gt[valid], minlength=Q))
+    assert torch.equal(counts.sum(0), torch.bincount(labels[valid].long(), minlength=Q))
+    assert int(labels.min()) >= 0 and int(labels.max()) < Q
+    again = zb.RunningScore(Q)
+    again.update(gt, labels)                                  # scoring the emitted labels separately
+    assert torch.equal(again.counts(), counts)
+    # first two images: independent generic kernel and the C oracle's decode on the same low-res logits
+    lowres = zb.ops.contraction(text, tokens[:2])
+    a = zb.ops.decode_score(lowres, (H, W), mode=_ffi.DECODE_GENERIC)
+    assert torch.equal(a, labels[:2])
+    if Q <= 128:
+        want = O.c_decode_semantic(lowres[:1].cpu().numpy(), (H, W))
+        assert np.array_equal(labels[:1].cpu().numpy().astype(np.int64), want)
+    ref_lo = torch.einsum("nc,bhwc->bnhw", text.double(), tokens[:2].double())
+    assert float((lowres.double() - ref_lo).abs().max() / ref_lo.abs().max()) <= 1e-5
+    s, _ = meter.get_scores()
+    assert 0.0 <= s["Mean IoU"] <= 1.0

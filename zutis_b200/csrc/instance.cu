@@ -1,0 +1,271 @@
+// Instance-path and on-request kernels (sm_100a):
+//   upsample_kernel         F.interpolate(...) materialised for return_logits=True   networks/zutis.py:366-370
+//   threshold_kernel        interp(probabilities) > threshold -> bit-packed masks    networks/zutis.py:422-425, :390
+//   unpack_bits_kernel      bit-packed -> one byte per pixel for legacy consumers
+//   pair_inter_kernel       popcount(mask_i & mask_j): the counts behind compute_iou  utils/iou.py:31-33 (NMS, zutis.py:258-259)
+//   lowres_stats_kernel     mask sizes, in-mask probability sums, masked mean tokens  networks/zutis.py:390-406
+//   categories_kernel       sigmoid(T * cos(text, mean token)) -> argmax / max        networks/zutis.py:409-420
+// Compiled with -fmad=false; interpolation uses the same explicit fma pattern as decode_score.cu.
+#include "common.cuh"
+
+namespace zutis {
+
+struct PlaneParams {
+    const float* in;
+    long sb, sq, sy, sx;
+    int B, Q, h, w, H, W;
+    float scale_y, scale_x;
+    int identity;
+};
+
+__device__ __forceinline__ float sample_bilinear(const PlaneParams& p, const float* plane, int Y, int X) {
+    if (p.identity) return __ldg(plane + (long)Y * p.sy + (long)X * p.sx);
+    const AxisTap ty = axis_tap(Y, p.h, p.H, p.scale_y);
+    const AxisTap tx = axis_tap(X, p.w, p.W, p.scale_x);
+    const float a = __ldg(plane + (long)ty.i0 * p.sy + (long)tx.i0 * p.sx);
+    const float b = __ldg(plane + (long)ty.i0 * p.sy + (long)tx.i1 * p.sx);
+    const float c = __ldg(plane + (long)ty.i1 * p.sy + (long)tx.i0 * p.sx);
+    const float d = __ldg(plane + (long)ty.i1 * p.sy + (long)tx.i1 * p.sx);
+    return __fmaf_rn(ty.l0, lerp_w(tx.l0, a, tx.l1, b), __fmul_rn(ty.l1, lerp_w(tx.l0, c, tx.l1, d)));
+}
+
+__global__ void __launch_bounds__(256) upsample_kernel(const PlaneParams p, float* out) {
+    const long total = (long)p.B * p.Q * p.H * p.W;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long r = i;
+        const int X = (int)(r % p.W); r /= p.W;
+        const int Y = (int)(r % p.H); r /= p.H;
+        const int q = (int)(r % p.Q);
+        const int b = (int)(r / p.Q);
+        out[i] = sample_bilinear(p, p.in + (long)b * p.sb + (long)q * p.sq, Y, X);
+    }
+}
+
+// one warp per (mask, output row, 32-pixel word)
+__global__ void __launch_bounds__(256) threshold_kernel(const PlaneParams p, float threshold, uint32_t* bits, int* areas) {
+    const int words = (p.W + 31) >> 5;
+    const long nwords = (long)p.B * p.Q * p.H * words;
+    const int lane = threadIdx.x & 31;
+    const long warp0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long wi = warp0; wi < nwords; wi += nwarps) {
+        long r = wi;
+        const int xw = (int)(r % words); r /= words;
+        const int Y = (int)(r % p.H); r /= p.H;      // r = b*Q + q
+        const int q = (int)(r % p.Q);
+        const int b = (int)(r / p.Q);
+        const int X = xw * 32 + lane;
+        bool on = false;
+        if (X < p.W) on = sample_bilinear(p, p.in + (long)b * p.sb + (long)q * p.sq, Y, X) > threshold;
+        const unsigned word = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) {
+            bits[wi] = word;
+            if (areas && word) atomicAdd(areas + r, __popc(word));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) unpack_bits_kernel(const uint32_t* bits, long n_masks, int H, int W, uint8_t* out) {
+    const int words = (W + 31) >> 5;
+    const long total = n_masks * H * W;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int X = (int)(i % W);
+        const long row = i / W;
+        out[i] = (bits[row * words + (X >> 5)] >> (X & 31)) & 1u;
+    }
+}
+
+// block (i, j>=i): inter[i][j] = inter[j][i] = sum_w popc(m_i[w] & m_j[w])
+__global__ void __launch_bounds__(256) pair_inter_kernel(const uint32_t* bits, int M, long words, int* inter) {
+    const int i = blockIdx.y, j = blockIdx.x;
+    if (j < i) return;
+    const uint32_t* a = bits + (long)i * words;
+    const uint32_t* c = bits + (long)j * words;
+    int acc = 0;
+    for (long k = threadIdx.x; k < words; k += blockDim.x) acc += __popc(a[k] & c[k]);
+    __shared__ int red[8];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int k = 0; k < 8; ++k) s += red[k];
+        inter[(long)i * M + j] = s;
+        inter[(long)j * M + i] = s;
+    }
+}
+
+// block per (b,q): size, probability sum and masked mean token.  Deterministic: fixed-order tree for the
+// scalar sums, ascending-pixel accumulation per channel for the token sum.
+__global__ void __launch_bounds__(256) lowres_stats_kernel(const float* probs, long sb, long sq, long sy, long sx,
+                                                           const float* tokens, int Q, int h, int w, int D, float threshold,
+                                                           int* sizes, float* psum, float* mean_tokens) {
+    extern __shared__ unsigned char s_mask[];      // [h*w] flags, then reduction scratch
+    const int bq = blockIdx.x;
+    const int b = bq / Q, q = bq % Q;
+    const int hw = h * w;
+    const float* plane = probs + (long)b * sb + (long)q * sq;
+    int cnt = 0;
+    float sum = 0.0f;
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+        const float v = plane[(long)(i / w) * sy + (long)(i % w) * sx];
+        const bool on = v > threshold;
+        s_mask[i] = on;
+        if (on) { ++cnt; sum = __fadd_rn(sum, v); }
+    }
+    __shared__ int r_cnt[8];
+    __shared__ float r_sum[8];
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+    }
+    if ((threadIdx.x & 31) == 0) { r_cnt[threadIdx.x >> 5] = cnt; r_sum[threadIdx.x >> 5] = sum; }
+    __syncthreads();
+    int total = 0;
+    float tsum = 0.0f;
+    for (int k = 0; k < 8; ++k) { total += r_cnt[k]; tsum = __fadd_rn(tsum, r_sum[k]); }
+    if (threadIdx.x == 0) { sizes[bq] = total; psum[bq] = tsum; }
+    if (mean_tokens) {
+        const float denom = __fadd_rn((float)total, 1e-7f);      // (mask_sizes + 1e-7) promotes to fp32, zutis.py:406
+        const float* tok = tokens + (long)b * hw * D;
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            float acc = 0.0f;
+            for (int i = 0; i < hw; ++i)
+                if (s_mask[i]) acc = __fadd_rn(acc, tok[(long)i * D + d]);
+            mean_tokens[(long)bq * D + d] = acc / denom;
+        }
+    }
+}
+
+// block per (b,q): cosine of the mean token with every text row, sigmoid(T*cos), first-max category.
+__global__ void __launch_bounds__(128) categories_kernel(const float* mean_tokens, const float* text, int n_cat, int D,
+                                                         float temperature, int* category, float* max_prob) {
+    extern __shared__ float s_tok[];               // [D] normalised token, then [n_cat] probabilities
+    float* s_prob = s_tok + D;
+    const int bq = blockIdx.x;
+    const float* t = mean_tokens + (long)bq * D;
+    float ss = 0.0f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) { const float v = t[d]; s_tok[d] = v; ss = __fmaf_rn(v, v, ss); }
+    __shared__ float red[4];
+    for (int o = 16; o > 0; o >>= 1) ss = __fadd_rn(ss, __shfl_xor_sync(0xffffffffu, ss, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    const float norm = __fadd_rn(sqrtf(__fadd_rn(__fadd_rn(red[0], red[1]), __fadd_rn(red[2], red[3]))), 1e-7f);   // zutis.py:412
+    for (int d = threadIdx.x; d < D; d += blockDim.x) s_tok[d] = s_tok[d] / norm;
+    __syncthreads();
+    for (int n = threadIdx.x; n < n_cat; n += blockDim.x) {
+        const float* e = text + (long)n * D;
+        float acc = 0.0f;
+        for (int d = 0; d < D; ++d) acc = __fmaf_rn(e[d], s_tok[d], acc);
+        const float z = __fmul_rn(acc, temperature);
+        s_prob[n] = 1.0f / (1.0f + expf(-z));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float best = s_prob[0];
+        int idx = 0;
+        for (int n = 1; n < n_cat; ++n)
+            if (better_nan_aware(s_prob[n], best)) { best = s_prob[n]; idx = n; }
+        category[bq] = idx;
+        max_prob[bq] = best;
+    }
+}
+
+static int make_plane_params(PlaneParams* p, const float* in, long sb, long sq, long sy, long sx,
+                             int B, int Q, int h, int w, int H, int W, const char* who) {
+    if (!in) return fail(ZUTIS_ERR_BAD_ARG, "%s: input is NULL", who);
+    if (!(B > 0 && Q > 0 && h > 0 && w > 0 && H > 0 && W > 0))
+        return fail(ZUTIS_ERR_BAD_ARG, "%s: non-positive shape B=%d Q=%d h=%d w=%d H=%d W=%d", who, B, Q, h, w, H, W);
+    p->in = in; p->sb = sb; p->sq = sq; p->sy = sy; p->sx = sx;
+    p->B = B; p->Q = Q; p->h = h; p->w = w; p->H = H; p->W = W;
+    p->scale_y = axis_scale(h, H); p->scale_x = axis_scale(w, W);
+    p->identity = (H == h && W == w);
+    return current_device_ok();
+}
+
+static unsigned grid_for(long work_items, int per_block) {
+    long blocks = (work_items + per_block - 1) / per_block;
+    const long cap = (long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+}  // namespace zutis
+
+using namespace zutis;
+
+extern "C" int zutis_upsample_bilinear(const float* in, long sb, long sq, long sy, long sx,
+                                       int B, int Q, int h, int w, int H, int W, float* out, void* stream) {
+    PlaneParams p;
+    int st = make_plane_params(&p, in, sb, sq, sy, sx, B, Q, h, w, H, W, "zutis_upsample_bilinear");
+    if (st != ZUTIS_OK) return st;
+    ZUTIS_REQUIRE(out != nullptr, "zutis_upsample_bilinear: out is NULL");
+    upsample_kernel<<<grid_for((long)B * Q * H * W, 256), 256, 0, (cudaStream_t)stream>>>(p, out);
+    return check_launch("upsample_kernel");
+}
+
+extern "C" int zutis_decode_threshold(const float* probs, long sb, long sq, long sy, long sx,
+                                      int B, int Q, int h, int w, int H, int W, float threshold,
+                                      uint32_t* mask_bits, int32_t* areas, void* stream) {
+    PlaneParams p;
+    int st = make_plane_params(&p, probs, sb, sq, sy, sx, B, Q, h, w, H, W, "zutis_decode_threshold");
+    if (st != ZUTIS_OK) return st;
+    ZUTIS_REQUIRE(mask_bits != nullptr, "zutis_decode_threshold: mask_bits is NULL");
+    const long nwords = (long)B * Q * H * ((W + 31) / 32);
+    threshold_kernel<<<grid_for(nwords, 8), 256, 0, (cudaStream_t)stream>>>(p, threshold, mask_bits, areas);
+    return check_launch("threshold_kernel");
+}
+
+extern "C" int zutis_unpack_mask_bits(const uint32_t* mask_bits, long n_masks, int H, int W,
+                                      uint8_t* out_bytes, void* stream) {
+    ZUTIS_REQUIRE(mask_bits && out_bytes, "zutis_unpack_mask_bits: NULL pointer");
+    ZUTIS_REQUIRE(n_masks >= 0 && H > 0 && W > 0, "zutis_unpack_mask_bits: bad shape");
+    int st = current_device_ok();
+    if (st != ZUTIS_OK) return st;
+    if (n_masks == 0) return ZUTIS_OK;
+    unpack_bits_kernel<<<grid_for(n_masks * H * W, 256), 256, 0, (cudaStream_t)stream>>>(mask_bits, n_masks, H, W, out_bytes);
+    return check_launch("unpack_bits_kernel");
+}
+
+extern "C" int zutis_pairwise_mask_intersections(const uint32_t* mask_bits, int M, long words_per_mask,
+                                                 int32_t* inter, void* stream) {
+    ZUTIS_REQUIRE(mask_bits && inter, "zutis_pairwise_mask_intersections: NULL pointer");
+    ZUTIS_REQUIRE(M > 0 && M <= 65535 && words_per_mask > 0, "zutis_pairwise_mask_intersections: bad shape M=%d words=%ld", M, words_per_mask);
+    int st = current_device_ok();
+    if (st != ZUTIS_OK) return st;
+    pair_inter_kernel<<<dim3(M, M), 256, 0, (cudaStream_t)stream>>>(mask_bits, M, words_per_mask, inter);
+    return check_launch("pair_inter_kernel");
+}
+
+extern "C" int zutis_instance_lowres_stats(const float* probs, long sb, long sq, long sy, long sx,
+                                           const float* tokens, int B, int Q, int h, int w, int D,
+                                           float threshold, int32_t* sizes, float* psum, float* mean_tokens,
+                                           void* stream) {
+    ZUTIS_REQUIRE(probs && sizes && psum, "zutis_instance_lowres_stats: NULL pointer");
+    ZUTIS_REQUIRE(B > 0 && Q > 0 && h > 0 && w > 0, "zutis_instance_lowres_stats: bad shape");
+    ZUTIS_REQUIRE(!mean_tokens || (tokens && D > 0), "zutis_instance_lowres_stats: mean_tokens needs tokens and D");
+    int st = current_device_ok();
+    if (st != ZUTIS_OK) return st;
+    const size_t smem = (size_t)h * w;
+    ZUTIS_REQUIRE(smem <= 200 * 1024, "zutis_instance_lowres_stats: h*w=%zu too large", smem);
+    if (smem > 48 * 1024)
+        ZUTIS_CUDA(cudaFuncSetAttribute(lowres_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lowres_stats_kernel<<<(unsigned)(B * Q), 256, smem, (cudaStream_t)stream>>>(probs, sb, sq, sy, sx, tokens, Q, h, w, D, threshold,
+                                                                                 sizes, psum, mean_tokens);
+    return check_launch("lowres_stats_kernel");
+}
+
+extern "C" int zutis_instance_categories(const float* mean_tokens, long n_rows, const float* text, int n_categories, int D,
+                                         float temperature, int32_t* category, float* max_prob, void* stream) {
+    ZUTIS_REQUIRE(mean_tokens && text && category && max_prob, "zutis_instance_categories: NULL pointer");
+    ZUTIS_REQUIRE(n_rows > 0 && n_categories > 0 && D > 0, "zutis_instance_categories: bad shape");
+    int st = current_device_ok();
+    if (st != ZUTIS_OK) return st;
+    const size_t smem = (size_t)(D + n_categories) * sizeof(float);
+    ZUTIS_REQUIRE(smem <= 200 * 1024, "zutis_instance_categories: D + n_categories too large");
+    if (smem > 48 * 1024)
+        ZUTIS_CUDA(cudaFuncSetAttribute(categories_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    categories_kernel<<<(unsigned)n_rows, 128, smem, (cudaStream_t)stream>>>(mean_tokens, text, n_categories, D, temperature, category, max_prob);
+    return check_launch("categories_kernel");
+}

@@ -1,0 +1,240 @@
+"""Drop-in for the decode half of the reference's ``networks/zutis.py``.
+
+``predict`` and ``get_mask_proposals`` keep the reference signatures and return types
+(networks/zutis.py:340-353 and :177-182) and are written to be bound onto the reference model::
+
+    from zutis_b200 import install; install(ZUTIS)      # ZUTIS.predict / get_mask_proposals now run on libzutis_b200
+
+or used through ``ZutisDecoder`` (an object holding only ``text_embeddings``).  ``forward`` is
+untouched.  What changes is what runs underneath:
+
+  semantic (zutis.py:355-372)  einsum -> tcgen05 / FFMA contraction kernel (pixel-major logits);
+                               F.interpolate + argmax -> one fused kernel that never writes the
+                               [B,Q,H,W] logits; the int16 device labels are widened to the int64
+                               numpy array the reference returns only at the very end.
+  instance (zutis.py:374-470)  low-res statistics, category decision, full-resolution thresholding
+                               into bit-packed masks and the pairwise intersections needed by NMS
+                               are kernels; the greedy NMS bookkeeping and the COCO-style dicts
+                               stay on the host like in the reference.
+
+Additive fast path (does not exist in the reference): ``decode_and_score`` feeds a
+``zutis_b200.RunningScore`` straight from the fused kernel, so neither labels nor logits leave
+the device.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from .running_score import RunningScore
+
+
+def _encode_rle(mask_fortran: np.ndarray):
+    """``pycocotools.mask.encode`` when available (as the reference uses, zutis.py:290), else the
+    equivalent uncompressed COCO RLE (column-major run lengths starting with the zero run)."""
+    try:
+        from pycocotools.mask import encode  # type: ignore
+        return encode(mask_fortran)
+    except ImportError:
+        flat = np.asarray(mask_fortran, dtype=np.uint8).ravel(order="F")
+        change = np.flatnonzero(np.diff(flat)) + 1
+        bounds = np.concatenate(([0], change, [flat.size]))
+        runs = np.diff(bounds).tolist()
+        if flat.size and flat[0] == 1:
+            runs = [0] + runs
+        return {"size": [int(mask_fortran.shape[0]), int(mask_fortran.shape[1])], "counts": runs}
+
+
+def _mask_to_box(mask: np.ndarray) -> List[float]:
+    """torchvision.ops.masks_to_boxes for one mask: [xmin, ymin, xmax, ymax] as floats (zutis.py:294)."""
+    ys, xs = np.nonzero(mask)
+    return [float(xs.min()), float(ys.min()), float(xs.max()), float(ys.max())]
+
+
+def _prediction(mask: np.ndarray, score: float, label_id: int, image_id, label_id_to_category) -> dict:
+    out = {
+        "category_id": label_id,
+        "segmentation": _encode_rle(np.asfortranarray(mask)),
+        "score": score,
+        "image_id": image_id,
+        "image_size": mask.shape[-2:],
+        "bbox": _mask_to_box(mask),
+    }
+    if label_id_to_category is not None:
+        out["pred_class"] = label_id_to_category[label_id]
+    return out
+
+
+def _nms_keep(cats: np.ndarray, scores: np.ndarray, inter: np.ndarray, nms_type: str, nms_threshold: float = 0.3,
+              sigma: float = 0.5, floor: float = 0.001) -> List[Tuple[np.integer, int, np.floating]]:
+    """Greedy per-category NMS of zutis.py:225-282 driven by pairwise intersection counts.
+
+    ``inter[i,j] = |m_i & m_j|`` (diagonal = areas) comes from the popcount kernel; the IoU is
+    ``inter / (area_i + area_j - inter + 1e-7)`` in float64 exactly as utils/iou.py:31-33 computes it.
+    Returns (category, query index, score) in the reference's emission order.
+    """
+    assert nms_type in ["hard", "linear", "gaussian"]
+    area = np.diag(inter).astype(np.int64)
+    kept = []
+    for cat in set(cats):
+        if cat == 0:                      # background category
+            continue
+        cand = list(np.nonzero(cats == cat)[0])
+        cand_scores = list(scores[cand])
+        chosen = []
+        while len(cand) > 0:
+            order = np.argsort(np.array(cand_scores))
+            cand = [cand[k] for k in order]
+            cand_scores = [cand_scores[k] for k in order]
+            top, top_score = cand[-1], cand_scores[-1]
+            chosen.append((top, top_score))
+            survivors, survivor_scores = [], []
+            for i, s in zip(cand[:-1], cand_scores[:-1]):
+                both = np.int64(inter[i, top])
+                iou = both / ((area[i] + area[top] - both) + 1e-7)
+                if nms_type == "hard":
+                    weight = 0 if iou > nms_threshold else 1
+                elif nms_type == "linear":
+                    weight = (1 - iou) if iou > nms_threshold else 1
+                else:
+                    weight = np.exp(-(iou * iou) / sigma)
+                s = s * weight
+                if s > floor:
+                    survivors.append(i); survivor_scores.append(s)
+            cand, cand_scores = survivors, survivor_scores
+        for i, s in chosen:
+            if area[i] == 0:
+                continue
+            kept.append((cat, int(i), s))
+    return kept
+
+
+@torch.no_grad()
+def predict(
+        self,
+        dict_outputs: dict,
+        mask_type: str,
+        threshold: float = 0.5,  # threshold for binarising an instance mask
+        image_ids: Optional[List[int]] = None,  # for COCO-style format
+        size: Optional[Tuple[int, int]] = None,  # (H, W) format
+        label_id_to_category: Optional[Dict[int, str]] = None,  # for instance segmentation
+        new_label_id_to_old_label_id: Optional[Dict[int, int]] = None,  # for coco labels
+        temperature: float = 5,
+        nms_type: str = "hard",
+        return_logits: bool = False,
+        precision: Optional[str] = None,
+):
+    """Same contract as ``ZUTIS.predict`` (networks/zutis.py:340-470); ``precision`` is additive."""
+    assert mask_type in ["semantic", "instance"]
+    text = self.text_embeddings
+    if mask_type == "semantic":
+        tokens = dict_outputs["patch_tokens"]                      # b x h x w x n_dims
+        lowres = ops.contraction(text.to(tokens.device), tokens, precision=precision)     # b x n x h x w
+        if return_logits:
+            # the one mode in which full-resolution logits are materialised, on request (zutis.py:369-370)
+            return ops.upsample_bilinear(lowres, size) if size is not None else lowres
+        labels = ops.decode_score(lowres, size)                    # int16 on the device
+        return labels.cpu().numpy().astype(np.int64)
+
+    mask_proposals: torch.Tensor = dict_outputs["mask_proposals"]
+    if len(mask_proposals.shape) == 5:
+        mask_proposals = mask_proposals[:, -1, ...]                # last decoder layer only (zutis.py:379-382)
+    lo, hi = torch.aminmax(mask_proposals)
+    assert 0 <= lo <= 1
+    assert 0 <= hi <= 1
+    tokens = dict_outputs["patch_tokens"]
+    B, Q, h, w = mask_proposals.shape
+
+    sizes, psum, mean_tokens = ops.instance_lowres_stats(mask_proposals, tokens, threshold)
+    cat_dev, prob_dev = ops.instance_categories(mean_tokens, text.to(tokens.device), temperature)
+    bits, _ = ops.decode_threshold(mask_proposals, size, threshold, want_areas=False)      # [B,Q,H,words]
+    H, W = ops.size_pair(size) if size is not None else (h, w)
+
+    # (sum of in-mask p) / (size + 1e-7) * max category probability, in fp32 like the reference (:396, :420)
+    sizes_h = sizes.cpu().numpy()
+    confidence = (psum.cpu().numpy() / (sizes_h.astype(np.float32) + np.float32(1e-7))) * prob_dev.cpu().numpy()
+    category_ids = cat_dev.cpu().numpy().astype(np.int64)
+
+    if image_ids is None:
+        image_ids = [0 for _ in range(B)]
+    predictions: List[dict] = list()
+    for b, image_id in zip(range(B), image_ids):
+        cats_b, conf_b = category_ids[b], confidence[b]
+        if nms_type is None:
+            areas = ops.pairwise_mask_intersections(bits[b]).diagonal().cpu().numpy()
+            keep = [(c, q, s) for q, (s, c) in enumerate(zip(conf_b, cats_b)) if areas[q] != 0 and c != 0]
+        else:
+            inter = ops.pairwise_mask_intersections(bits[b]).cpu().numpy()
+            keep = _nms_keep(cats_b, conf_b, inter, nms_type)
+        if not keep:
+            continue
+        chosen = torch.as_tensor([q for _, q, _ in keep], device=bits.device)
+        masks = ops.unpack_mask_bits(bits[b].index_select(0, chosen), W).cpu().numpy()
+        for (c, q, s), m in zip(keep, masks):
+            label_id = new_label_id_to_old_label_id[c.item()] if new_label_id_to_old_label_id is not None else c.item()
+            predictions.append(_prediction(m, s.item(), label_id, image_id, label_id_to_category))
+    return predictions
+
+
+def get_mask_proposals(self, queries: torch.Tensor, patch_tokens: torch.Tensor, return_binary_masks: bool = True,
+                       precision: Optional[str] = None):
+    """Same contract as ``ZUTIS.get_mask_proposals`` (networks/zutis.py:177-209).
+
+    queries [B,Q,C] or [B,L,Q,C]; patch_tokens [B,h,w,C] -> sigmoid(queries . tokens) of shape
+    [B,(L,)Q,h,w]; the sigmoid is fused into the contraction kernel's epilogue.  With
+    ``return_binary_masks`` (no caller in the reference) the raw products and one-hot argmax masks
+    are returned instead, as the reference does.
+    """
+    if len(queries.shape) not in (3, 4):
+        raise ValueError(f"{len(queries.shape)} not in [3, 4]")
+    B = queries.shape[0]
+    h, w = patch_tokens.shape[1:3]
+    lead = tuple(queries.shape[1:-1])                                 # (Q,) or (L,Q)
+    flat = queries.reshape(B, -1, queries.shape[-1])
+    if return_binary_masks:
+        raw = ops.contraction(flat, patch_tokens, precision=precision, pixel_major=False)
+        raw = raw.view(B, *lead, h, w)
+        n_queries = lead[-1]
+        per_group = raw.reshape(-1, n_queries, h, w)
+        winners = ops.decode_score(per_group, None).view(B, *lead[:-1], h, w)
+        ids = torch.arange(n_queries, device=raw.device, dtype=winners.dtype).view(*([1] * len(lead[:-1])), n_queries, 1, 1)
+        one_hot = winners.unsqueeze(-3) == ids.unsqueeze(0)
+        return raw, one_hot
+    out = ops.contraction(flat, patch_tokens, precision=precision, sigmoid=True, pixel_major=False)
+    return out.view(B, *lead, h, w)
+
+
+def decode_and_score(text: torch.Tensor, patch_tokens: torch.Tensor, label_trues, size, meter: RunningScore,
+                     want_labels: bool = False, precision: Optional[str] = None):
+    """Fused semantic evaluation step: contraction -> (upsample, argmax, confusion counts) on the device.
+
+    Equivalent to ``meter.update(label_trues, predict(..., "semantic", size=size))``
+    (trainer.py:331-347) without materialising logits or labels on the host.
+    """
+    lowres = ops.contraction(text, patch_tokens, precision=precision)
+    return meter.update_from_logits(lowres, label_trues, size=size, want_labels=want_labels)
+
+
+class ZutisDecoder:
+    """The decode half of the model as a standalone object (only ``text_embeddings`` is needed)."""
+
+    def __init__(self, text_embeddings: torch.Tensor):
+        if not text_embeddings.is_cuda:
+            raise TypeError("text_embeddings must live on a CUDA device (zutis_b200 has no CPU path)")
+        self.text_embeddings = text_embeddings.detach().float().contiguous()
+
+    predict = predict
+    get_mask_proposals = get_mask_proposals
+
+    def decode_and_score(self, patch_tokens, label_trues, size, meter: RunningScore, want_labels: bool = False,
+                         precision: Optional[str] = None):
+        return decode_and_score(self.text_embeddings, patch_tokens, label_trues, size, meter, want_labels, precision)
+
+
+def install(zutis_cls) -> None:
+    """Bind the B200 decode path onto the reference model class (``networks.zutis.ZUTIS``)."""
+    zutis_cls.predict = predict
+    zutis_cls.get_mask_proposals = get_mask_proposals

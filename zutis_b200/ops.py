@@ -1,0 +1,243 @@
+"""Tensor-level wrappers over the C ABI: torch owns memory and streams, the kernels do the work.
+
+Every function here takes CUDA tensors, passes raw pointers + element strides to
+libzutis_b200.so on the caller's current stream, and returns CUDA tensors.  Nothing in this
+module computes with torch ops.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _ffi as F
+
+_GT_CODES = {torch.uint8: F.GT_U8, torch.int16: F.GT_I16, torch.int32: F.GT_I32, torch.int64: F.GT_I64}
+_PRECISIONS = {"fp32": F.GEMM_FP32_SIMT, "tf32x3": F.GEMM_TF32X3, "bf16": F.GEMM_BF16}
+
+# Contraction precision used when the caller does not choose.  "auto" = the tcgen05 kernel with the
+# 3-term error-compensated TF32 split (fp32-grade, needed for the 99.99 % label bar) whenever the
+# shape qualifies (K % 32 == 0, aligned K-contiguous rows), else the fp32 FFMA kernel.  Both are
+# sm_100a CUDA kernels of this library; neither is a library or CPU fallback.
+DEFAULT_PRECISION = "auto"
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA tensor (zutis_b200 has no CPU path)")
+
+
+def size_pair(size) -> Optional[Tuple[int, int]]:
+    """(H, W) from (int,int), a torch.Size slice or a pair of 1-element tensors (trainer.py:322-325)."""
+    if size is None:
+        return None
+    H, W = size
+    return int(H), int(W)
+
+
+def gemm_flags(precision: Optional[str], sigmoid: bool = False) -> int:
+    p = DEFAULT_PRECISION if precision is None else precision
+    if p == "auto":
+        p = "tf32x3"
+    if p not in _PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}, got {p!r}")
+    return _PRECISIONS[p] | (F.GEMM_SIGMOID if sigmoid else 0)
+
+
+def contraction(a: torch.Tensor, feats: torch.Tensor, *, precision: Optional[str] = None, sigmoid: bool = False,
+                pixel_major: bool = True) -> torch.Tensor:
+    """out[b,n,y,x] = act(sum_c a[(b,)n,c] * feats[b,y,x,c])   (zutis.py:361-365, :184-186 + :209).
+
+    a: [M,C] shared by the batch (text embeddings) or [B,M,C] per image (queries).
+    feats: [B,h,w,C] channel-last.  Returns a [B,M,h,w] tensor; with ``pixel_major`` its memory
+    is [B,h,w,Mp] (category index contiguous, Mp = M rounded up to 4) -- the layout the fused
+    decode kernel streams -- otherwise it is a contiguous [B,M,h,w].
+    """
+    _need_cuda(a, "a"); _need_cuda(feats, "feats")
+    if feats.dim() != 4:
+        raise ValueError(f"feats must be [B,h,w,C], got {tuple(feats.shape)}")
+    a = a.float(); feats = feats.float()
+    if feats.stride(-1) != 1 or feats.stride(1) != feats.shape[2] * feats.stride(2) or feats.stride(0) != feats.shape[1] * feats.stride(1):
+        feats = feats.contiguous()
+    if a.stride(-1) != 1:
+        a = a.contiguous()
+    B, h, w, Cc = feats.shape
+    shared = a.dim() == 2
+    if not shared and (a.dim() != 3 or a.shape[0] != B):
+        raise ValueError(f"a must be [M,C] or [B,M,C] with B={B}, got {tuple(a.shape)}")
+    if not shared and a.stride(0) != a.shape[1] * a.stride(1):
+        a = a.contiguous()
+    M = a.shape[-2]
+    if a.shape[-1] != Cc:
+        raise ValueError(f"contraction width mismatch: {a.shape[-1]} vs {Cc}")
+    N = h * w
+    flags = gemm_flags(precision, sigmoid)
+    if pixel_major:
+        Mp = (M + 3) & ~3
+        buf = torch.empty((B, h, w, Mp), device=feats.device, dtype=torch.float32)
+        if Mp != M:
+            buf[..., M:].zero_()
+        s_cn, s_cp, s_c = 1, Mp, N * Mp
+        out = buf[..., :M].permute(0, 3, 1, 2)
+    else:
+        buf = torch.empty((B, M, h, w), device=feats.device, dtype=torch.float32)
+        s_cn, s_cp, s_c = N, 1, M * N
+        out = buf
+    def launch(fl: int) -> None:
+        ws_bytes = F.lib().zutis_gemm_workspace_bytes(M, N, Cc, B, fl)
+        ws = torch.empty(ws_bytes, device=feats.device, dtype=torch.uint8) if ws_bytes else None
+        with torch.cuda.device(feats.device):
+            F.call("zutis_gemm_logits", a.data_ptr(), a.stride(-2), 0 if shared else a.stride(0),
+                   feats.data_ptr(), feats.stride(2), feats.stride(0),
+                   buf.data_ptr(), s_cn, s_cp, s_c, M, N, Cc, B, fl,
+                   ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
+
+    if (precision or DEFAULT_PRECISION) == "auto":
+        try:
+            launch(gemm_flags("tf32x3", sigmoid))
+        except F.ZutisUnsupported:
+            launch(gemm_flags("fp32", sigmoid))
+    else:
+        launch(flags)
+    return out
+
+
+def decode_score(logits: torch.Tensor, size=None, *, gt: Optional[torch.Tensor] = None,
+                 hist_partial: Optional[torch.Tensor] = None, n_classes: Optional[int] = None,
+                 want_labels: bool = True, mode: int = F.DECODE_AUTO) -> Optional[torch.Tensor]:
+    """Fused upsample -> argmax -> (labels, confusion counts)   (zutis.py:366-372 + running_score.py:10-16).
+
+    logits [B,Q,h,w] fp32 with any strides; gt [B,H,W] integer CUDA tensor (or None);
+    hist_partial int32 [n_classes*n_classes] accumulated into.  Returns int16 labels [B,H,W] or None.
+    """
+    _need_cuda(logits, "logits")
+    if logits.dim() != 4 or logits.dtype != torch.float32:
+        raise ValueError(f"logits must be fp32 [B,Q,h,w], got {logits.dtype} {tuple(logits.shape)}")
+    B, Q, h, w = logits.shape
+    hw = size_pair(size)
+    H, W = hw if hw is not None else (h, w)
+    labels = torch.empty((B, H, W), device=logits.device, dtype=torch.int16) if want_labels else None
+    gt_ptr, gt_code, gt_sb = None, F.GT_I64, H * W
+    if hist_partial is not None:
+        if gt is None:
+            raise ValueError("hist_partial needs gt")
+        _need_cuda(gt, "gt"); _need_cuda(hist_partial, "hist_partial")
+        if gt.dtype not in _GT_CODES:
+            raise TypeError(f"gt dtype {gt.dtype} not supported (uint8/int16/int32/int64)")
+        if tuple(gt.shape) != (B, H, W):
+            raise ValueError(f"gt must be [B,H,W]={B, H, W}, got {tuple(gt.shape)}")
+        if gt.stride(2) != 1 or gt.stride(1) != W:
+            gt = gt.contiguous()
+        gt_ptr, gt_code, gt_sb = gt.data_ptr(), _GT_CODES[gt.dtype], gt.stride(0) if B > 1 else H * W
+        n_classes = Q if n_classes is None else n_classes
+        if hist_partial.dtype != torch.int32 or hist_partial.numel() != n_classes * n_classes or not hist_partial.is_contiguous():
+            raise ValueError("hist_partial must be a contiguous int32 tensor with n_classes^2 elements")
+    with torch.cuda.device(logits.device):
+        F.call("zutis_decode_score", logits.data_ptr(), logits.stride(0), logits.stride(1), logits.stride(2), logits.stride(3),
+               B, Q, h, w, H, W, gt_ptr, gt_code, gt_sb,
+               labels.data_ptr() if labels is not None else None,
+               hist_partial.data_ptr() if hist_partial is not None else None,
+               n_classes if hist_partial is not None else 0, mode, _stream())
+    return labels
+
+
+def score_labels(gt: torch.Tensor, pred: torch.Tensor, hist_partial: torch.Tensor, n_classes: int) -> None:
+    """RunningScore._fast_hist on device labels (any supported integer dtypes, same element count)."""
+    _need_cuda(gt, "gt"); _need_cuda(pred, "pred"); _need_cuda(hist_partial, "hist_partial")
+    if gt.dtype not in _GT_CODES or pred.dtype not in _GT_CODES:
+        raise TypeError(f"label dtypes must be uint8/int16/int32/int64, got {gt.dtype}, {pred.dtype}")
+    gt = gt.contiguous(); pred = pred.contiguous()
+    if gt.numel() != pred.numel():
+        raise ValueError(f"gt and pred differ in size: {gt.numel()} vs {pred.numel()}")
+    with torch.cuda.device(gt.device):
+        F.call("zutis_score_labels", gt.data_ptr(), _GT_CODES[gt.dtype], pred.data_ptr(), _GT_CODES[pred.dtype],
+               gt.numel(), hist_partial.data_ptr(), n_classes, _stream())
+
+
+def hist_merge(partials: torch.Tensor, hist_i64: torch.Tensor, clear: bool = True) -> None:
+    n2 = hist_i64.numel()
+    with torch.cuda.device(hist_i64.device):
+        F.call("zutis_hist_merge", partials.data_ptr(), partials.numel() // n2, hist_i64.data_ptr(), n2, int(clear), _stream())
+
+
+def upsample_bilinear(x: torch.Tensor, size) -> torch.Tensor:
+    """F.interpolate(x, size, mode="bilinear") materialised (return_logits=True, zutis.py:366-370)."""
+    _need_cuda(x, "x")
+    B, Q, h, w = x.shape
+    H, W = size_pair(size)
+    out = torch.empty((B, Q, H, W), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        F.call("zutis_upsample_bilinear", x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), x.stride(3),
+               B, Q, h, w, H, W, out.data_ptr(), _stream())
+    return out
+
+
+def decode_threshold(probs: torch.Tensor, size=None, threshold: float = 0.5, want_areas: bool = True):
+    """interp(probs) > threshold as bit-packed masks uint32-in-int32 [B,Q,H,words] (+ int32 areas [B,Q])."""
+    _need_cuda(probs, "probs")
+    B, Q, h, w = probs.shape
+    hw = size_pair(size)
+    H, W = hw if hw is not None else (h, w)
+    words = (W + 31) // 32
+    bits = torch.empty((B, Q, H, words), device=probs.device, dtype=torch.int32)
+    areas = torch.zeros((B, Q), device=probs.device, dtype=torch.int32) if want_areas else None
+    with torch.cuda.device(probs.device):
+        F.call("zutis_decode_threshold", probs.data_ptr(), probs.stride(0), probs.stride(1), probs.stride(2), probs.stride(3),
+               B, Q, h, w, H, W, float(threshold), bits.data_ptr(), areas.data_ptr() if areas is not None else None, _stream())
+    return bits, areas
+
+
+def unpack_mask_bits(bits: torch.Tensor, W: int) -> torch.Tensor:
+    """bit-packed [...,H,words] -> bool [...,H,W]."""
+    H = bits.shape[-2]
+    n = bits.numel() // (H * bits.shape[-1])
+    out = torch.empty(bits.shape[:-2] + (H, W), device=bits.device, dtype=torch.uint8)
+    if n:
+        with torch.cuda.device(bits.device):
+            F.call("zutis_unpack_mask_bits", bits.contiguous().data_ptr(), n, H, W, out.data_ptr(), _stream())
+    return out.view(torch.bool)
+
+
+def pairwise_mask_intersections(bits: torch.Tensor) -> torch.Tensor:
+    """bits [M,H,words] -> int32 [M,M] with popcount(m_i & m_j) (diagonal = areas)."""
+    M = bits.shape[0]
+    words = bits.numel() // M
+    inter = torch.empty((M, M), device=bits.device, dtype=torch.int32)
+    with torch.cuda.device(bits.device):
+        F.call("zutis_pairwise_mask_intersections", bits.contiguous().data_ptr(), M, words, inter.data_ptr(), _stream())
+    return inter
+
+
+def instance_lowres_stats(probs: torch.Tensor, tokens: Optional[torch.Tensor], threshold: float = 0.5):
+    """sizes int32 [B,Q], psum fp32 [B,Q], mean_tokens fp32 [B,Q,D]   (zutis.py:390-406)."""
+    _need_cuda(probs, "probs")
+    B, Q, h, w = probs.shape
+    sizes = torch.empty((B, Q), device=probs.device, dtype=torch.int32)
+    psum = torch.empty((B, Q), device=probs.device, dtype=torch.float32)
+    mean = None
+    D = 0
+    if tokens is not None:
+        tokens = tokens.float().contiguous()
+        D = tokens.shape[-1]
+        mean = torch.empty((B, Q, D), device=probs.device, dtype=torch.float32)
+    with torch.cuda.device(probs.device):
+        F.call("zutis_instance_lowres_stats", probs.data_ptr(), probs.stride(0), probs.stride(1), probs.stride(2), probs.stride(3),
+               tokens.data_ptr() if tokens is not None else None, B, Q, h, w, D, float(threshold),
+               sizes.data_ptr(), psum.data_ptr(), mean.data_ptr() if mean is not None else None, _stream())
+    return sizes, psum, mean
+
+
+def instance_categories(mean_tokens: torch.Tensor, text: torch.Tensor, temperature: float = 5.0):
+    """category int32 [B,Q], max_prob fp32 [B,Q]   (zutis.py:409-420)."""
+    B, Q, D = mean_tokens.shape
+    text = text.float().contiguous()
+    cat = torch.empty((B, Q), device=mean_tokens.device, dtype=torch.int32)
+    prob = torch.empty((B, Q), device=mean_tokens.device, dtype=torch.float32)
+    with torch.cuda.device(mean_tokens.device):
+        F.call("zutis_instance_categories", mean_tokens.contiguous().data_ptr(), B * Q, text.data_ptr(), text.shape[0], D,
+               float(temperature), cat.data_ptr(), prob.data_ptr(), _stream())
+    return cat, prob

@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--iid", action="store_true", help="spatially independent tokens (adversarial for pruning)")
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x3", "bf16"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x3", "tf32"])
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -355,7 +355,7 @@ def run_ours(args, cfg, rank, local, world):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {cfg['desc']}", "tokens": "iid" if args.iid else "model-like (x2-upsampled coarse features)",
                    "gt_dtype": "int64", "images_per_gpu_per_step": B, "parallelism": f"dp{world} (images sharded, one int64 all-reduce at the end)",
-                   "contraction": {0: "fp32 FFMA", 1: "tcgen05 3xTF32", 2: "tcgen05 bf16"}[flags & 3],
+                   "contraction": {0: "fp32 FFMA", 1: "tcgen05 3xTF32", 2: "tcgen05 TF32 single pass"}[flags & 3],
                    "l2_policy": f"{n_sets} rotating input sets of {tok_bytes / 1e6:.0f} MB tokens each (> 126 MB L2 between reuses)"},
         "clocks": clocks,
         "e2e": e2e,

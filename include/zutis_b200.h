@@ -58,7 +58,7 @@ typedef enum {
 enum {
     ZUTIS_GEMM_FP32_SIMT = 0,      /* fp32 FFMA kernel (exact fp32 products, fp32 accumulate) */
     ZUTIS_GEMM_TF32X3 = 1,         /* tcgen05 kind::tf32, 3-term error-compensated split (fp32-grade) */
-    ZUTIS_GEMM_BF16 = 2,           /* tcgen05 kind::f16 on bf16-rounded operands (2e-2 logit bar only) */
+    ZUTIS_GEMM_TF32 = 2,           /* tcgen05 kind::tf32, single pass (reduced precision: meets the 2e-2 logit bar only) */
     ZUTIS_GEMM_PRECISION_MASK = 3,
     ZUTIS_GEMM_SIGMOID = 16        /* fused sigmoid epilogue (zutis.py:209) */
 };

@@ -52,7 +52,7 @@ def tie_gap_ok(full_ref: np.ndarray, a: np.ndarray, b: np.ndarray, ulps: float =
 
 
 # ------------------------------------------------------------------------------ contraction
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("auto", 1e-5)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("auto", 1e-5), ("tf32x3", 1e-5), ("tf32", 2e-2)])
 def test_contraction_model_cfg1(zb, golden, precision, tol):
     g = golden("model_cfg1")
     out = zb.ops.contraction(dev(g["text"]), dev(g["tokens"]), precision=precision)
@@ -62,6 +62,34 @@ def test_contraction_model_cfg1(zb, golden, precision, tol):
     assert np.abs(out.cpu().numpy() - ref).max() / np.abs(ref).max() <= tol
     out2 = zb.ops.contraction(dev(g["text"]), dev(g["tokens"]), precision=precision, pixel_major=False)
     assert out2.is_contiguous() and torch.equal(out2, out.contiguous())
+    if precision == "tf32":
+        # the single-pass mode really is reduced precision (it must NOT be what feeds labels)
+        assert np.abs(out.cpu().numpy() - ref).max() / np.abs(ref).max() > 1e-5
+
+
+def test_tcgen05_path_is_taken_and_matches_fp32_kernel(zb):
+    """K % 32 == 0 shapes run on the tensor-core kernel; compare with the FFMA kernel and float64."""
+    gen = torch.Generator().manual_seed(8)
+    for (B, M, h, w, K) in [(3, 81, 40, 40, 512), (2, 920, 9, 11, 512), (2, 100, 15, 20, 768), (1, 16, 3, 5, 32), (2, 257, 12, 12, 64)]:
+        text = torch.nn.functional.normalize(torch.randn(M, K, generator=gen), dim=-1).cuda()
+        tok = torch.nn.functional.normalize(torch.randn(B, h, w, K, generator=gen), dim=-1).cuda()
+        ref = torch.einsum("nc,bhwc->bnhw", text.double(), tok.double())
+        scale = float(ref.abs().max())
+        for pm in (True, False):
+            tc = zb.ops.contraction(text, tok, precision="tf32x3", pixel_major=pm)
+            ff = zb.ops.contraction(text, tok, precision="fp32", pixel_major=pm)
+            assert float((tc.double() - ref).abs().max()) / scale <= 2e-6, (B, M, h, w, K, pm)
+            assert float((ff.double() - ref).abs().max()) / scale <= 2e-6
+        one = zb.ops.contraction(text, tok, precision="tf32")
+        assert 1e-5 < float((one.double() - ref).abs().max()) / scale <= 2e-2
+    # per-image A operand (queries) with the fused sigmoid epilogue
+    q = torch.nn.functional.normalize(torch.randn(3, 100, 768, generator=gen), dim=-1).cuda()
+    feats = torch.randn(3, 15, 20, 768, generator=gen).cuda()
+    ref = torch.sigmoid(torch.einsum("bqc,bhwc->bqhw", q.double(), feats.double()))
+    got = zb.ops.contraction(q, feats, precision="tf32x3", sigmoid=True, pixel_major=False)
+    assert float((got.double() - ref).abs().max()) <= 2e-6
+    with pytest.raises(zb.ZutisUnsupported):
+        zb.ops.contraction(torch.randn(5, 24).cuda(), torch.randn(1, 4, 4, 24).cuda(), precision="tf32x3")   # K % 32 != 0
 
 
 @pytest.mark.parametrize("name", ["int8x", "nonint", "x16", "wideq"])

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libzutis_b200.so")
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE, ERR_NO_DEVICE = range(6)
 GT_U8, GT_I16, GT_I32, GT_I64 = range(4)
 DECODE_AUTO, DECODE_GENERIC, DECODE_TILED, DECODE_PRUNED = range(4)
-GEMM_FP32_SIMT, GEMM_TF32X3, GEMM_BF16 = 0, 1, 2
+GEMM_FP32_SIMT, GEMM_TF32X3, GEMM_TF32 = 0, 1, 2
 GEMM_SIGMOID = 16
 
 

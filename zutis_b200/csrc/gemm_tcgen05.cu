@@ -12,18 +12,21 @@
 // and  D += hi*hi + hi*lo + lo*hi  goes into ONE fp32 TMEM accumulator (dropped lo*lo term ~ 2^-22).
 //   * The category operand (81..920 rows) is split once per call by split_operand_kernel into a
 //     zero-padded workspace [hi | lo] and arrives by TMA.
-//   * The pixel operand is split IN SHARED MEMORY: TMA lands the raw fp32 tile, four converter warps
-//     rewrite it in place as `hi` and write `lo` to a sibling buffer (the transform is element-wise,
-//     so it is oblivious to the 128B swizzle), fence.proxy.async, then hand the stage to the MMA warp.
+//   * The pixel operand is split ON ITS WAY INTO TENSOR MEMORY: TMA lands the raw fp32 tile in shared
+//     memory, eight converter warps read it once (un-swizzling their own row), and tcgen05.st the `hi`
+//     and `lo` halves into per-stage TMEM columns; the MMAs then take A from TMEM (tcgen05.mma [d],[a],b)
+//     and only the category operand B is ever re-read from shared memory.  (r01c measured the previous
+//     all-in-smem variant as shared-memory-port bound: 172 KB moved per K slab; this moves 92 KB.)
 //   ZUTIS_GEMM_TF32 runs the single pass hi*hi only: the reduced-precision mode that meets the 2e-2 logit bar.
 //
-// Warp roles (384 threads, 1 CTA / SM, persistent over tiles):
+// Warp roles (512 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0      TMA producer (one elected lane)        waits empty[s]      -> arms full_raw[s]
 //   warp 1      MMA issuer  (one elected lane)         waits full_cvt[s], tmem_empty[a] -> commits empty[s], tmem_full[a]
 //   warp 2      TMEM allocator / deallocator
 //   warps 4-7   epilogue: tcgen05.ld -> (sigmoid) -> global stores, any (stride_cn, stride_cp)
-//   warps 8-11  converters (hi/lo split of the pixel tile)
-// Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warps 8-15  converters: smem raw tile -> (hi, lo) -> tcgen05.st into the stage's TMEM columns
+// TMEM map (512 columns): [0, acc_bufs*umma_n) accumulators (double-buffered when they fit, so the epilogue
+// of tile i overlaps the MMAs of tile i+1), then per stage 32 columns of A_hi and 32 of A_lo.
 #include "gemm.cuh"
 
 #include <cuda.h>
@@ -38,8 +41,9 @@ constexpr int BLOCK_M = 128;          // pixels per tile (UMMA M)
 constexpr int BLOCK_K = 32;           // fp32 per slab = 128 bytes = one swizzle row
 constexpr int UMMA_K = 8;             // tf32 MMA K
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;     // 16 KB
-constexpr int NUM_THREADS = 384;
-constexpr int MAX_STAGES = 4;
+constexpr int NUM_THREADS = 512;
+constexpr int MAX_STAGES = 5;
+constexpr int NUM_CONVERTERS = 256;   // threads
 constexpr int SMEM_LIMIT = 232448;    // 227 KB opt-in maximum per CTA
 
 struct TcParams {
@@ -56,6 +60,8 @@ struct TcParams {
     int stages;
     int stage_bytes;
     int tmem_cols;
+    int acc_bufs;     // accumulator buffers in TMEM (2 when they fit next to the A stages)
+    int a_col0;       // first TMEM column of the per-stage A operand (64 columns per stage: hi | lo)
     int passes;       // 3 = hi*hi + hi*lo + lo*hi, 1 = hi*hi only
     int sigmoid;
 };
@@ -87,7 +93,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!done);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -109,17 +114,25 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 
-// D[tmem] (+)= A[smem] * B[smem], kind::tf32, single CTA
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem], kind::tf32, single CTA: the A operand lives in tensor memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
         "}\n"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -192,10 +205,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
     const int b_tile_bytes = p.umma_n * BLOCK_K * 4;
 
     // shared-memory map: stages | barriers | tmem pointer
-    auto stage_a_hi = [&](int s) { return base + (uint32_t)s * p.stage_bytes; };
-    auto stage_a_lo = [&](int s) { return base + (uint32_t)s * p.stage_bytes + A_TILE_BYTES; };
-    auto stage_b_hi = [&](int s) { return base + (uint32_t)s * p.stage_bytes + 2 * A_TILE_BYTES; };
-    auto stage_b_lo = [&](int s) { return base + (uint32_t)s * p.stage_bytes + 2 * A_TILE_BYTES + b_tile_bytes; };
+    auto stage_a_raw = [&](int s) { return base + (uint32_t)s * p.stage_bytes; };
+    auto stage_b_hi = [&](int s) { return base + (uint32_t)s * p.stage_bytes + A_TILE_BYTES; };
+    auto stage_b_lo = [&](int s) { return base + (uint32_t)s * p.stage_bytes + A_TILE_BYTES + b_tile_bytes; };
     const uint32_t bar_base = base + (uint32_t)p.stages * p.stage_bytes;
     auto bar_full_raw = [&](int s) { return bar_base + 8u * s; };
     auto bar_full_cvt = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
@@ -208,7 +220,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
         prefetch_tmap(&map_pix); prefetch_tmap(&map_cat_hi); prefetch_tmap(&map_cat_lo);
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(bar_full_raw(s), 1);
-            mbar_init(bar_full_cvt(s), 128);
+            mbar_init(bar_full_cvt(s), NUM_CONVERTERS);
             mbar_init(bar_empty(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -244,7 +256,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
                     const uint32_t ph = (it / p.stages) & 1;
                     mbar_wait(bar_empty(s), ph ^ 1);
                     mbar_arrive_expect_tx(bar_full_raw(s), stage_tx);
-                    tma_load_2d(stage_a_hi(s), &map_pix, bar_full_raw(s), kb * BLOCK_K, pix_row);
+                    tma_load_2d(stage_a_raw(s), &map_pix, bar_full_raw(s), kb * BLOCK_K, pix_row);
                     tma_load_2d(stage_b_hi(s), &map_cat_hi, bar_full_raw(s), kb * BLOCK_K, cat_row);
                     if (p.passes == 3) tma_load_2d(stage_b_lo(s), &map_cat_lo, bar_full_raw(s), kb * BLOCK_K, cat_row);
                 }
@@ -256,8 +268,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
             const uint32_t idesc = make_idesc_tf32(BLOCK_M, p.umma_n);
             uint32_t it = 0, acc_it = 0;
             for (long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++acc_it) {
-                const int a = acc_it & 1;
-                const uint32_t aph = (acc_it >> 1) & 1;
+                const int a = acc_it % p.acc_bufs;
+                const uint32_t aph = (acc_it / p.acc_bufs) & 1;
                 mbar_wait(bar_tmem_empty(a), aph ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(a * p.umma_n);
@@ -266,20 +278,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
                     const uint32_t ph = (it / p.stages) & 1;
                     mbar_wait(bar_full_cvt(s), ph);
                     tc_fence_after();
-                    const uint64_t a_hi = make_desc_sw128(stage_a_hi(s));
-                    const uint64_t a_lo = make_desc_sw128(stage_a_lo(s));
+                    const uint32_t a_hi = tmem_base + (uint32_t)(p.a_col0 + s * 64);
+                    const uint32_t a_lo = a_hi + 32;
                     const uint64_t b_hi = make_desc_sw128(stage_b_hi(s));
                     const uint64_t b_lo = make_desc_sw128(stage_b_lo(s));
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);      // +32 bytes per k-step inside the swizzle row
-                        umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_tf32_ts(tmem_d, a_hi + k * UMMA_K, b_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
                         if (p.passes == 3) {
-                            umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
-                            umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+                            umma_tf32_ts(tmem_d, a_hi + k * UMMA_K, b_lo + adv, idesc, 1u);
+                            umma_tf32_ts(tmem_d, a_lo + k * UMMA_K, b_hi + adv, idesc, 1u);
                         }
                     }
-                    umma_commit(bar_empty(s));          // stage s may be refilled once these MMAs retire
+                    umma_commit(bar_empty(s));          // stage s (smem B, raw A, TMEM A columns) may be refilled once these MMAs retire
                 }
                 umma_commit(bar_tmem_full(a));          // accumulator a is complete
             }
@@ -293,8 +305,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
             const long r = t / p.n_tiles;
             const int pt = (int)(r % p.p_tiles);
             const int b = (int)(r / p.p_tiles);
-            const int a = acc_it & 1;
-            const uint32_t aph = (acc_it >> 1) & 1;
+            const int a = acc_it % p.acc_bufs;
+            const uint32_t aph = (acc_it / p.acc_bufs) & 1;
             mbar_wait(bar_tmem_full(a), aph);
             tc_fence_after();
             const long pix = (long)pt * BLOCK_M + quad * 32 + lane;
@@ -337,31 +349,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
         }
     } else if (warp >= 8) {
         // =============================== converters ===============================
-        const int tid = threadIdx.x - 256;              // 0..127
+        // Thread = one pixel row of the tile (TMEM lane) and one half of the 32-wide K slab.  Row m of the
+        // TMA-written tile lives at m*128 bytes with its 16-byte chunks XOR-swizzled by (m & 7).
+        const int quad = warp & 3;                      // TMEM lanes [32*quad, 32*quad+32)
+        const int half = (warp - 8) >> 2;               // K columns [16*half, 16*half+16)
+        const int row = quad * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         uint32_t it = 0;
         for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             for (int kb = 0; kb < num_k; ++kb, ++it) {
                 const int s = it % p.stages;
                 const uint32_t ph = (it / p.stages) & 1;
                 mbar_wait(bar_full_raw(s), ph);
-                const uint32_t hi_base = stage_a_hi(s), lo_base = stage_a_lo(s);
+                const uint32_t row_base = stage_a_raw(s) + (uint32_t)row * 128u;
+                uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int j = 0; j < A_TILE_BYTES / 16 / 128; ++j) {
-                    const uint32_t off = (uint32_t)(j * 128 + tid) * 16u;
-                    float x0, x1, x2, x3;
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3) : "r"(hi_base + off));
-                    const uint32_t h0 = to_tf32_rn(x0), h1 = to_tf32_rn(x1), h2 = to_tf32_rn(x2), h3 = to_tf32_rn(x3);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + off), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
-                    if (p.passes == 3) {
-                        const float big = 3.402823466e38f;
-                        const uint32_t l0 = to_tf32_rn(fabsf(x0) <= big ? __fsub_rn(x0, __uint_as_float(h0)) : 0.0f);
-                        const uint32_t l1 = to_tf32_rn(fabsf(x1) <= big ? __fsub_rn(x1, __uint_as_float(h1)) : 0.0f);
-                        const uint32_t l2 = to_tf32_rn(fabsf(x2) <= big ? __fsub_rn(x2, __uint_as_float(h2)) : 0.0f);
-                        const uint32_t l3 = to_tf32_rn(fabsf(x3) <= big ? __fsub_rn(x3, __uint_as_float(h3)) : 0.0f);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo_base + off), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t chunk = (uint32_t)((half * 4 + c) ^ (row & 7));
+                    float x[4];
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]) : "r"(row_base + chunk * 16u));
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t h = to_tf32_rn(x[e]);
+                        hi[c * 4 + e] = h;
+                        lo[c * 4 + e] = to_tf32_rn(fabsf(x[e]) <= 3.402823466e38f ? __fsub_rn(x[e], __uint_as_float(h)) : 0.0f);
                     }
                 }
-                fence_proxy_async_smem();               // generic-proxy writes -> visible to tcgen05.mma (async proxy)
+                const uint32_t col = (uint32_t)(p.a_col0 + s * 64 + half * 16);
+                tmem_st_x16(tmem_base + lane_addr + col, hi);
+                if (p.passes == 3) tmem_st_x16(tmem_base + lane_addr + col + 32, lo);
+                tmem_st_wait();
+                tc_fence_before();
                 mbar_arrive(bar_full_cvt(s));
             }
         }
@@ -410,7 +428,7 @@ int make_map(CUtensorMap* map, const void* ptr, long rows, int K, long ld, int b
 }
 
 struct Plan {
-    int n_tiles, umma_n, rows_per_image, stages, stage_bytes, tmem_cols;
+    int n_tiles, umma_n, rows_per_image, stages, stage_bytes, tmem_cols, acc_bufs, a_col0;
 };
 
 Plan make_plan(int M) {
@@ -419,12 +437,16 @@ Plan make_plan(int M) {
     const int per = (M + pl.n_tiles - 1) / pl.n_tiles;
     pl.umma_n = (per + 15) & ~15;
     pl.rows_per_image = pl.n_tiles * pl.umma_n;
-    pl.stage_bytes = 2 * A_TILE_BYTES + 2 * pl.umma_n * BLOCK_K * 4;
+    pl.stage_bytes = A_TILE_BYTES + 2 * pl.umma_n * BLOCK_K * 4;
     pl.stages = (SMEM_LIMIT - 1024 - 256) / pl.stage_bytes;
     if (pl.stages > MAX_STAGES) pl.stages = MAX_STAGES;
-    int cols = 32;
-    while (cols < 2 * pl.umma_n) cols <<= 1;
-    pl.tmem_cols = cols;
+    pl.tmem_cols = 512;
+    // TMEM: accumulators first, then 64 columns of A (hi | lo) per stage.  Double-buffer the accumulator when
+    // at least 3 stages still fit beside it.
+    pl.acc_bufs = (((2 * pl.umma_n + 31) & ~31) + 3 * 64 <= 512) ? 2 : 1;
+    pl.a_col0 = (pl.acc_bufs * pl.umma_n + 31) & ~31;
+    const int tmem_stages = (512 - pl.a_col0) / 64;
+    if (pl.stages > tmem_stages) pl.stages = tmem_stages;
     return pl;
 }
 
@@ -479,7 +501,7 @@ int launch_gemm_tcgen05(const GemmParams& g, int batch, int flags, void* workspa
     p.M = g.M; p.N = g.N; p.K = g.K; p.batch = batch;
     p.umma_n = pl.umma_n; p.n_tiles = pl.n_tiles; p.p_tiles = (int)((g.N + BLOCK_M - 1) / BLOCK_M);
     p.a_rows_per_image = shared_a ? 0 : pl.rows_per_image;
-    p.stages = pl.stages; p.stage_bytes = pl.stage_bytes; p.tmem_cols = pl.tmem_cols;
+    p.stages = pl.stages; p.stage_bytes = pl.stage_bytes; p.tmem_cols = pl.tmem_cols; p.acc_bufs = pl.acc_bufs; p.a_col0 = pl.a_col0;
     p.passes = ((flags & ZUTIS_GEMM_PRECISION_MASK) == ZUTIS_GEMM_TF32X3) ? 3 : 1;
     p.sigmoid = g.sigmoid;
 

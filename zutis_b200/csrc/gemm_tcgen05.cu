@@ -153,6 +153,14 @@ __device__ __forceinline__ uint32_t to_tf32_rn(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return u;
 }
+// Same rounding (nearest, ties away) for the converter warps' inner loop, spelled so that it costs one FMA-pipe
+// integer add and one LOP3 instead of cvt.rna's four ALU-pipe instructions (the ALU pipe is half rate on sm_100
+// and was the contraction kernel's limiter).  +inf stays +inf; NaN stays NaN unless its payload is all ones.
+__device__ __forceinline__ uint32_t to_tf32_rn_fast(float x) {
+    uint32_t u;
+    asm("mad.lo.u32 %0, %1, 1, 0x1000;" : "=r"(u) : "r"(__float_as_uint(x)));
+    return u & 0xffffe000u;
+}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 //   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major; 1) | [32,46) SBO >> 4 = 1024 B between
@@ -243,7 +251,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
     if (warp == 0) {
         // ============================== TMA producer ==============================
         if (lane == 0) {
-            uint32_t it = 0;
+            int s = 0;
+            uint32_t ph = 0;
             for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int nt = (int)(t % p.n_tiles);
                 const long r = t / p.n_tiles;
@@ -251,14 +260,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
                 const int b = (int)(r / p.p_tiles);
                 const int pix_row = (int)((long)b * p.N + (long)pt * BLOCK_M);
                 const int cat_row = b * p.a_rows_per_image + nt * p.umma_n;
-                for (int kb = 0; kb < num_k; ++kb, ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (it / p.stages) & 1;
+                for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(bar_empty(s), ph ^ 1);
                     mbar_arrive_expect_tx(bar_full_raw(s), stage_tx);
                     tma_load_2d(stage_a_raw(s), &map_pix, bar_full_raw(s), kb * BLOCK_K, pix_row);
                     tma_load_2d(stage_b_hi(s), &map_cat_hi, bar_full_raw(s), kb * BLOCK_K, cat_row);
                     if (p.passes == 3) tma_load_2d(stage_b_lo(s), &map_cat_lo, bar_full_raw(s), kb * BLOCK_K, cat_row);
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -266,16 +274,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
         // =============================== MMA issuer ===============================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(BLOCK_M, p.umma_n);
-            uint32_t it = 0, acc_it = 0;
+            uint32_t acc_it = 0;
+            int s = 0;
+            uint32_t ph = 0;
             for (long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++acc_it) {
                 const int a = acc_it % p.acc_bufs;
                 const uint32_t aph = (acc_it / p.acc_bufs) & 1;
                 mbar_wait(bar_tmem_empty(a), aph ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(a * p.umma_n);
-                for (int kb = 0; kb < num_k; ++kb, ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (it / p.stages) & 1;
+                for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(bar_full_cvt(s), ph);
                     tc_fence_after();
                     const uint32_t a_hi = tmem_base + (uint32_t)(p.a_col0 + s * 64);
@@ -292,6 +300,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
                         }
                     }
                     umma_commit(bar_empty(s));          // stage s (smem B, raw A, TMEM A columns) may be refilled once these MMAs retire
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
                 umma_commit(bar_tmem_full(a));          // accumulator a is complete
             }
@@ -355,11 +364,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
         const int half = (warp - 8) >> 2;               // K columns [16*half, 16*half+16)
         const int row = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        uint32_t it = 0;
+        int s = 0;
+        uint32_t ph = 0;
         for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            for (int kb = 0; kb < num_k; ++kb, ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (it / p.stages) & 1;
+            for (int kb = 0; kb < num_k; ++kb) {
                 mbar_wait(bar_full_raw(s), ph);
                 const uint32_t row_base = stage_a_raw(s) + (uint32_t)row * 128u;
                 uint32_t hi[16], lo[16];
@@ -370,9 +378,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]) : "r"(row_base + chunk * 16u));
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const uint32_t h = to_tf32_rn(x[e]);
+                        // x = hi + lo exactly (x - hi is exact in fp32); lo is then rounded to tf32 as well.
+                        // A +-inf token gives lo = NaN, i.e. NaN logits where the reference has +-inf.
+                        const uint32_t h = to_tf32_rn_fast(x[e]);
                         hi[c * 4 + e] = h;
-                        lo[c * 4 + e] = to_tf32_rn(fabsf(x[e]) <= 3.402823466e38f ? __fsub_rn(x[e], __uint_as_float(h)) : 0.0f);
+                        lo[c * 4 + e] = to_tf32_rn_fast(__fsub_rn(x[e], __uint_as_float(h)));
                     }
                 }
                 const uint32_t col = (uint32_t)(p.a_col0 + s * 64 + half * 16);
@@ -381,6 +391,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(bar_full_cvt(s));
+                if (++s == p.stages) { s = 0; ph ^= 1; }
             }
         }
     }

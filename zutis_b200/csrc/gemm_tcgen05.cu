@@ -19,14 +19,20 @@
 //     all-in-smem variant as shared-memory-port bound: 172 KB moved per K slab; this moves 92 KB.)
 //   ZUTIS_GEMM_TF32 runs the single pass hi*hi only: the reduced-precision mode that meets the 2e-2 logit bar.
 //
-// Warp roles (512 threads, 1 CTA / SM, persistent over tiles):
-//   warp 0      TMA producer (one elected lane)        waits empty[s]      -> arms full_raw[s]
-//   warp 1      MMA issuer  (one elected lane)         waits full_cvt[s], tmem_empty[a] -> commits empty[s], tmem_full[a]
+// Warp roles (512 threads, 1 CTA / SM, persistent over tiles) and the three decoupled rings they run:
+//   warp 0      pixel-tile TMA producer   A ring  (smem, SA slots of 16 KB):  waits a_free[i]  -> arms a_full[i]
+//   warp 3      category TMA producer     B ring  (smem, SB slots hi|lo):    waits b_free[j]  -> arms b_full[j]
+//   warps 8-15  converters                A ring -> T ring: wait a_full[i], t_free[k]; ld.shared; arrive a_free[i]
+//                                         (the smem slot is free as soon as the row sits in registers); split;
+//                                         tcgen05.st; arrive t_ready[k]
+//   warp 1      MMA issuer (one lane)     waits t_ready[k], b_full[j], tmem_empty[a]; 3 MMAs per k-step;
+//                                         commits t_free[k], b_free[j], and tmem_full[a] after the last slab
 //   warp 2      TMEM allocator / deallocator
 //   warps 4-7   epilogue: tcgen05.ld -> (sigmoid) -> global stores, any (stride_cn, stride_cp)
-//   warps 8-15  converters: smem raw tile -> (hi, lo) -> tcgen05.st into the stage's TMEM columns
+// Decoupling matters: with one ring the HBM stream of pixel tiles had to wait for MMA completion + commit
+// before every refill and the kernel was latency-bound at ~1400 cycles per slab whatever the MMA count.
 // TMEM map (512 columns): [0, acc_bufs*umma_n) accumulators (double-buffered when they fit, so the epilogue
-// of tile i overlaps the MMAs of tile i+1), then per stage 32 columns of A_hi and 32 of A_lo.
+// of tile i overlaps the MMAs of tile i+1), then ST slots of 64 columns (A_hi | A_lo).
 #include "gemm.cuh"
 
 #include <cuda.h>
@@ -42,7 +48,7 @@ constexpr int BLOCK_K = 32;           // fp32 per slab = 128 bytes = one swizzle
 constexpr int UMMA_K = 8;             // tf32 MMA K
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;     // 16 KB
 constexpr int NUM_THREADS = 512;
-constexpr int MAX_STAGES = 5;
+constexpr int MAX_A = 8, MAX_B = 5, MAX_T = 5;   // ring depth limits
 constexpr int NUM_CONVERTERS = 256;   // threads
 constexpr int SMEM_LIMIT = 232448;    // 227 KB opt-in maximum per CTA
 
@@ -57,8 +63,8 @@ struct TcParams {
     int n_tiles;      // N tiles
     int p_tiles;      // pixel tiles per image
     int a_rows_per_image;   // rows of the split workspace per image (0 => shared by the batch)
-    int stages;
-    int stage_bytes;
+    int sa, sb, st;   // ring depths: smem pixel tiles, smem category tiles, TMEM split-pixel slots
+    int b_slot_bytes;
     int tmem_cols;
     int acc_bufs;     // accumulator buffers in TMEM (2 when they fit next to the A stages)
     int a_col0;       // first TMEM column of the per-stage A operand (64 columns per stage: hi | lo)
@@ -91,6 +97,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
     } while (!done);
+}
+// one lane of a CONVERGED warp; tcgen05.mma / commit / TMA issued under this predicate compile to a single
+// UTCHMMA / UTCBAR / UTMALDG (inside `if (lane == 0)` the compiler wraps each in an elect-and-retry loop, which
+// made the one-thread MMA issuer the kernel's critical path)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -212,29 +232,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
     const int lane = threadIdx.x & 31;
     const int b_tile_bytes = p.umma_n * BLOCK_K * 4;
 
-    // shared-memory map: stages | barriers | tmem pointer
-    auto stage_a_raw = [&](int s) { return base + (uint32_t)s * p.stage_bytes; };
-    auto stage_b_hi = [&](int s) { return base + (uint32_t)s * p.stage_bytes + A_TILE_BYTES; };
-    auto stage_b_lo = [&](int s) { return base + (uint32_t)s * p.stage_bytes + A_TILE_BYTES + b_tile_bytes; };
-    const uint32_t bar_base = base + (uint32_t)p.stages * p.stage_bytes;
-    auto bar_full_raw = [&](int s) { return bar_base + 8u * s; };
-    auto bar_full_cvt = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
-    auto bar_empty = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
-    auto bar_tmem_full = [&](int a) { return bar_base + 8u * (3 * MAX_STAGES + a); };
-    auto bar_tmem_empty = [&](int a) { return bar_base + 8u * (3 * MAX_STAGES + 2 + a); };
-    const uint32_t tmem_slot = bar_base + 8u * (3 * MAX_STAGES + 4);
+    // shared-memory map: A ring | B ring | barriers | tmem pointer
+    auto slot_a = [&](int i) { return base + (uint32_t)i * A_TILE_BYTES; };
+    const uint32_t b_base = base + (uint32_t)p.sa * A_TILE_BYTES;
+    auto slot_b_hi = [&](int j) { return b_base + (uint32_t)j * p.b_slot_bytes; };
+    auto slot_b_lo = [&](int j) { return b_base + (uint32_t)j * p.b_slot_bytes + b_tile_bytes; };
+    const uint32_t bar_base = b_base + (uint32_t)p.sb * p.b_slot_bytes;
+    auto bar_a_full = [&](int i) { return bar_base + 8u * i; };
+    auto bar_a_free = [&](int i) { return bar_base + 8u * (MAX_A + i); };
+    auto bar_b_full = [&](int j) { return bar_base + 8u * (2 * MAX_A + j); };
+    auto bar_b_free = [&](int j) { return bar_base + 8u * (2 * MAX_A + MAX_B + j); };
+    auto bar_t_ready = [&](int k) { return bar_base + 8u * (2 * MAX_A + 2 * MAX_B + k); };
+    auto bar_t_free = [&](int k) { return bar_base + 8u * (2 * MAX_A + 2 * MAX_B + MAX_T + k); };
+    auto bar_tmem_full = [&](int a) { return bar_base + 8u * (2 * MAX_A + 2 * MAX_B + 2 * MAX_T + a); };
+    auto bar_tmem_empty = [&](int a) { return bar_base + 8u * (2 * MAX_A + 2 * MAX_B + 2 * MAX_T + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_A + 2 * MAX_B + 2 * MAX_T + 4);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_pix); prefetch_tmap(&map_cat_hi); prefetch_tmap(&map_cat_lo);
-        for (int s = 0; s < p.stages; ++s) {
-            mbar_init(bar_full_raw(s), 1);
-            mbar_init(bar_full_cvt(s), NUM_CONVERTERS);
-            mbar_init(bar_empty(s), 1);
-        }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(bar_tmem_full(a), 1);
-            mbar_init(bar_tmem_empty(a), 128);
-        }
+        for (int i = 0; i < p.sa; ++i) { mbar_init(bar_a_full(i), 1); mbar_init(bar_a_free(i), NUM_CONVERTERS); }
+        for (int j = 0; j < p.sb; ++j) { mbar_init(bar_b_full(j), 1); mbar_init(bar_b_free(j), 1); }
+        for (int k = 0; k < p.st; ++k) { mbar_init(bar_t_ready(k), NUM_CONVERTERS); mbar_init(bar_t_free(k), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tmem_full(a), 1); mbar_init(bar_tmem_empty(a), 128); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -246,37 +265,55 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
 
     const int num_k = p.K / BLOCK_K;
     const long total_tiles = (long)p.batch * p.p_tiles * p.n_tiles;
-    const uint32_t stage_tx = (uint32_t)A_TILE_BYTES + (p.passes == 3 ? 2u : 1u) * (uint32_t)b_tile_bytes;
 
     if (warp == 0) {
-        // ============================== TMA producer ==============================
-        if (lane == 0) {
-            int s = 0;
+        // ========================= pixel-tile TMA producer (A ring) =========================
+        {
+            int i = 0;
             uint32_t ph = 0;
             for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int nt = (int)(t % p.n_tiles);
                 const long r = t / p.n_tiles;
-                const int pt = (int)(r % p.p_tiles);
-                const int b = (int)(r / p.p_tiles);
-                const int pix_row = (int)((long)b * p.N + (long)pt * BLOCK_M);
+                const int pix_row = (int)((long)(r / p.p_tiles) * p.N + (long)(r % p.p_tiles) * BLOCK_M);
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(bar_a_free(i), ph ^ 1);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(bar_a_full(i), (uint32_t)A_TILE_BYTES);
+                        tma_load_2d(slot_a(i), &map_pix, bar_a_full(i), kb * BLOCK_K, pix_row);
+                    }
+                    __syncwarp();
+                    if (++i == p.sa) { i = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ========================= category TMA producer (B ring) ==========================
+        {
+            int j = 0;
+            uint32_t ph = 0;
+            const uint32_t tx = (p.passes == 3 ? 2u : 1u) * (uint32_t)b_tile_bytes;
+            for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int nt = (int)(t % p.n_tiles);
+                const int b = (int)((t / p.n_tiles) / p.p_tiles);
                 const int cat_row = b * p.a_rows_per_image + nt * p.umma_n;
                 for (int kb = 0; kb < num_k; ++kb) {
-                    mbar_wait(bar_empty(s), ph ^ 1);
-                    mbar_arrive_expect_tx(bar_full_raw(s), stage_tx);
-                    tma_load_2d(stage_a_raw(s), &map_pix, bar_full_raw(s), kb * BLOCK_K, pix_row);
-                    tma_load_2d(stage_b_hi(s), &map_cat_hi, bar_full_raw(s), kb * BLOCK_K, cat_row);
-                    if (p.passes == 3) tma_load_2d(stage_b_lo(s), &map_cat_lo, bar_full_raw(s), kb * BLOCK_K, cat_row);
-                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                    mbar_wait(bar_b_free(j), ph ^ 1);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(bar_b_full(j), tx);
+                        tma_load_2d(slot_b_hi(j), &map_cat_hi, bar_b_full(j), kb * BLOCK_K, cat_row);
+                        if (p.passes == 3) tma_load_2d(slot_b_lo(j), &map_cat_lo, bar_b_full(j), kb * BLOCK_K, cat_row);
+                    }
+                    __syncwarp();
+                    if (++j == p.sb) { j = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
-        if (lane == 0) {
+        {
             const uint32_t idesc = make_idesc_tf32(BLOCK_M, p.umma_n);
             uint32_t acc_it = 0;
-            int s = 0;
-            uint32_t ph = 0;
+            int j = 0, k = 0;
+            uint32_t phj = 0, phk = 0;
             for (long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++acc_it) {
                 const int a = acc_it % p.acc_bufs;
                 const uint32_t aph = (acc_it / p.acc_bufs) & 1;
@@ -284,25 +321,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(a * p.umma_n);
                 for (int kb = 0; kb < num_k; ++kb) {
-                    mbar_wait(bar_full_cvt(s), ph);
+                    mbar_wait(bar_b_full(j), phj);
+                    mbar_wait(bar_t_ready(k), phk);
                     tc_fence_after();
-                    const uint32_t a_hi = tmem_base + (uint32_t)(p.a_col0 + s * 64);
+                    const uint32_t a_hi = tmem_base + (uint32_t)(p.a_col0 + k * 64);
                     const uint32_t a_lo = a_hi + 32;
-                    const uint64_t b_hi = make_desc_sw128(stage_b_hi(s));
-                    const uint64_t b_lo = make_desc_sw128(stage_b_lo(s));
+                    const uint64_t b_hi = make_desc_sw128(slot_b_hi(j));
+                    const uint64_t b_lo = make_desc_sw128(slot_b_lo(j));
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);      // +32 bytes per k-step inside the swizzle row
-                        umma_tf32_ts(tmem_d, a_hi + k * UMMA_K, b_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
-                        if (p.passes == 3) {
-                            umma_tf32_ts(tmem_d, a_hi + k * UMMA_K, b_lo + adv, idesc, 1u);
-                            umma_tf32_ts(tmem_d, a_lo + k * UMMA_K, b_hi + adv, idesc, 1u);
+                        for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+                            const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4); // +32 bytes per k-step inside the swizzle row
+                            umma_tf32_ts(tmem_d, a_hi + kk * UMMA_K, b_hi + adv, idesc, (kb | kk) != 0 ? 1u : 0u);
+                            if (p.passes == 3) {
+                                umma_tf32_ts(tmem_d, a_hi + kk * UMMA_K, b_lo + adv, idesc, 1u);
+                                umma_tf32_ts(tmem_d, a_lo + kk * UMMA_K, b_hi + adv, idesc, 1u);
+                            }
                         }
+                        umma_commit(bar_t_free(k));     // TMEM slot k and smem slot j may be refilled once these MMAs retire
+                        umma_commit(bar_b_free(j));
                     }
-                    umma_commit(bar_empty(s));          // stage s (smem B, raw A, TMEM A columns) may be refilled once these MMAs retire
-                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                    __syncwarp();
+                    if (++j == p.sb) { j = 0; phj ^= 1; }
+                    if (++k == p.st) { k = 0; phk ^= 1; }
                 }
-                umma_commit(bar_tmem_full(a));          // accumulator a is complete
+                if (elect_one()) umma_commit(bar_tmem_full(a));      // accumulator a is complete
+                __syncwarp();
             }
         }
     } else if (warp >= 4 && warp < 8) {
@@ -329,27 +373,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
                 tmem_ld_wait();
                 const int n0 = nt * p.umma_n + c * 16;
                 if (row_ok && n0 < p.M) {
-                float f[16];
+                    float f[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    f[j] = __uint_as_float(v[j]);
-                    if (p.sigmoid) f[j] = sigmoidf_exact(f[j]);
-                }
-                if (vec_ok) {
-                    // pixel-major rows: padding columns up to the row pitch hold zeros (zero-padded operand rows)
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        if (n0 + j + 3 < p.stride_cp && n0 + j < p.M)
-                            *reinterpret_cast<float4*>(crow + n0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                        else
-                            for (int e = 0; e < 4; ++e)
-                                if (n0 + j + e < p.M) crow[n0 + j + e] = f[j + e];
+                    for (int j = 0; j < 16; ++j) {
+                        f[j] = __uint_as_float(v[j]);
+                        if (p.sigmoid) f[j] = sigmoidf_exact(f[j]);
                     }
-                } else {
+                    if (vec_ok) {
+                        // pixel-major rows: padding columns up to the row pitch hold zeros (zero-padded operand rows)
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (n0 + j < p.M) crow[(long)(n0 + j) * p.stride_cn] = f[j];
-                }
+                        for (int j = 0; j < 16; j += 4) {
+                            if (n0 + j + 3 < p.stride_cp && n0 + j < p.M)
+                                *reinterpret_cast<float4*>(crow + n0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                            else
+                                for (int e = 0; e < 4; ++e)
+                                    if (n0 + j + e < p.M) crow[n0 + j + e] = f[j + e];
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n0 + j < p.M) crow[(long)(n0 + j) * p.stride_cn] = f[j];
+                    }
                 }
                 __syncwarp();
             }
@@ -364,34 +408,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
         const int half = (warp - 8) >> 2;               // K columns [16*half, 16*half+16)
         const int row = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        int s = 0;
-        uint32_t ph = 0;
+        int i = 0, k = 0;
+        uint32_t phi = 0, phk = 0;
         for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             for (int kb = 0; kb < num_k; ++kb) {
-                mbar_wait(bar_full_raw(s), ph);
-                const uint32_t row_base = stage_a_raw(s) + (uint32_t)row * 128u;
-                uint32_t hi[16], lo[16];
+                mbar_wait(bar_a_full(i), phi);
+                const uint32_t row_base = slot_a(i) + (uint32_t)row * 128u;
+                float x[16];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const uint32_t chunk = (uint32_t)((half * 4 + c) ^ (row & 7));
-                    float x[4];
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]) : "r"(row_base + chunk * 16u));
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        // x = hi + lo exactly (x - hi is exact in fp32); lo is then rounded to tf32 as well.
-                        // A +-inf token gives lo = NaN, i.e. NaN logits where the reference has +-inf.
-                        const uint32_t h = to_tf32_rn_fast(x[e]);
-                        hi[c * 4 + e] = h;
-                        lo[c * 4 + e] = to_tf32_rn_fast(__fsub_rn(x[e], __uint_as_float(h)));
-                    }
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(x[c * 4]), "=f"(x[c * 4 + 1]), "=f"(x[c * 4 + 2]), "=f"(x[c * 4 + 3]) : "r"(row_base + chunk * 16u));
                 }
-                const uint32_t col = (uint32_t)(p.a_col0 + s * 64 + half * 16);
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    // x = hi + lo exactly (x - hi is exact in fp32); lo is then rounded to tf32 as well.
+                    // A +-inf token gives lo = NaN, i.e. NaN logits where the reference has +-inf.
+                    hi[e] = to_tf32_rn_fast(x[e]);
+                    lo[e] = to_tf32_rn_fast(__fsub_rn(x[e], __uint_as_float(hi[e])));
+                }
+                mbar_arrive(bar_a_free(i));             // the row is in registers: the smem slot can be refilled
+                if (++i == p.sa) { i = 0; phi ^= 1; }
+                mbar_wait(bar_t_free(k), phk ^ 1);
+                tc_fence_after();
+                const uint32_t col = (uint32_t)(p.a_col0 + k * 64 + half * 16);
                 tmem_st_x16(tmem_base + lane_addr + col, hi);
                 if (p.passes == 3) tmem_st_x16(tmem_base + lane_addr + col + 32, lo);
                 tmem_st_wait();
                 tc_fence_before();
-                mbar_arrive(bar_full_cvt(s));
-                if (++s == p.stages) { s = 0; ph ^= 1; }
+                mbar_arrive(bar_t_ready(k));
+                if (++k == p.st) { k = 0; phk ^= 1; }
             }
         }
     }
@@ -439,7 +487,8 @@ int make_map(CUtensorMap* map, const void* ptr, long rows, int K, long ld, int b
 }
 
 struct Plan {
-    int n_tiles, umma_n, rows_per_image, stages, stage_bytes, tmem_cols, acc_bufs, a_col0;
+    int n_tiles, umma_n, rows_per_image, sa, sb, st, b_slot_bytes, tmem_cols, acc_bufs, a_col0;
+    size_t smem;
 };
 
 Plan make_plan(int M) {
@@ -448,16 +497,20 @@ Plan make_plan(int M) {
     const int per = (M + pl.n_tiles - 1) / pl.n_tiles;
     pl.umma_n = (per + 15) & ~15;
     pl.rows_per_image = pl.n_tiles * pl.umma_n;
-    pl.stage_bytes = A_TILE_BYTES + 2 * pl.umma_n * BLOCK_K * 4;
-    pl.stages = (SMEM_LIMIT - 1024 - 256) / pl.stage_bytes;
-    if (pl.stages > MAX_STAGES) pl.stages = MAX_STAGES;
+    pl.b_slot_bytes = 2 * pl.umma_n * BLOCK_K * 4;
+    const int budget = SMEM_LIMIT - 1024 - 512;                       // alignment slack, barriers
+    pl.sb = (budget - 3 * A_TILE_BYTES) / pl.b_slot_bytes;
+    if (pl.sb > MAX_B) pl.sb = MAX_B;
+    pl.sa = pl.sb >= 1 ? (budget - pl.sb * pl.b_slot_bytes) / A_TILE_BYTES : 0;
+    if (pl.sa > MAX_A) pl.sa = MAX_A;
     pl.tmem_cols = 512;
-    // TMEM: accumulators first, then 64 columns of A (hi | lo) per stage.  Double-buffer the accumulator when
-    // at least 3 stages still fit beside it.
+    // TMEM: accumulators first, then 64 columns (A_hi | A_lo) per slot.  Double-buffer the accumulator when
+    // at least 3 slots still fit beside it.
     pl.acc_bufs = (((2 * pl.umma_n + 31) & ~31) + 3 * 64 <= 512) ? 2 : 1;
     pl.a_col0 = (pl.acc_bufs * pl.umma_n + 31) & ~31;
-    const int tmem_stages = (512 - pl.a_col0) / 64;
-    if (pl.stages > tmem_stages) pl.stages = tmem_stages;
+    pl.st = (512 - pl.a_col0) / 64;
+    if (pl.st > MAX_T) pl.st = MAX_T;
+    pl.smem = (size_t)pl.sa * A_TILE_BYTES + (size_t)pl.sb * pl.b_slot_bytes + 1024 + 512;
     return pl;
 }
 
@@ -475,7 +528,7 @@ bool gemm_tcgen05_supports(const GemmParams& g, int batch, int flags) {
     if ((g.ldb & 3) != 0 || (reinterpret_cast<uintptr_t>(g.Bm) & 15) != 0) return false;
     if (batch > 1 && g.strideB != g.N * g.ldb) return false;        // images must be consecutive rows of one 2-D tensor
     if ((long)batch * g.N >= 2147483647L) return false;
-    if (make_plan(g.M).stages < 2) return false;
+    { const Plan pl = make_plan(g.M); if (pl.sa < 2 || pl.sb < 2 || pl.st < 2) return false; }
     return true;
 }
 
@@ -512,11 +565,11 @@ int launch_gemm_tcgen05(const GemmParams& g, int batch, int flags, void* workspa
     p.M = g.M; p.N = g.N; p.K = g.K; p.batch = batch;
     p.umma_n = pl.umma_n; p.n_tiles = pl.n_tiles; p.p_tiles = (int)((g.N + BLOCK_M - 1) / BLOCK_M);
     p.a_rows_per_image = shared_a ? 0 : pl.rows_per_image;
-    p.stages = pl.stages; p.stage_bytes = pl.stage_bytes; p.tmem_cols = pl.tmem_cols; p.acc_bufs = pl.acc_bufs; p.a_col0 = pl.a_col0;
+    p.sa = pl.sa; p.sb = pl.sb; p.st = pl.st; p.b_slot_bytes = pl.b_slot_bytes; p.tmem_cols = pl.tmem_cols; p.acc_bufs = pl.acc_bufs; p.a_col0 = pl.a_col0;
     p.passes = ((flags & ZUTIS_GEMM_PRECISION_MASK) == ZUTIS_GEMM_TF32X3) ? 3 : 1;
     p.sigmoid = g.sigmoid;
 
-    const size_t smem = (size_t)pl.stages * pl.stage_bytes + 1024 + 256;
+    const size_t smem = pl.smem;
     ZUTIS_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long total_tiles = (long)batch * p.p_tiles * p.n_tiles;
     const unsigned grid = (unsigned)(total_tiles < sms ? total_tiles : sms);

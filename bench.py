@@ -315,6 +315,13 @@ def run_ours(args, cfg, rank, local, world):
     meter.all_reduce()
     scores, _ = meter.get_scores()
     total_px = int(meter.counts().sum().item())
+    # integrity of the timed path (untimed): the last step's logits against the fp32 FFMA kernel on every image, and
+    # its labels against the generic decode kernel
+    last_tokens = sets[(args.steps - 1) % n_sets][1]
+    exact = ops.contraction(text, last_tokens, precision="fp32")
+    logit_err = float(((logits - exact).abs().amax(dim=(1, 2, 3)) / exact.abs().max()).max().item())
+    relabel = ops.decode_score(logits, (H, W), mode=_ffi.DECODE_GENERIC)
+    label_mismatch = int((relabel != labels).sum().item())
 
     # ---- e2e: host (pinned) buffers through the C ABI's host entry, copies inside the timed region
     e2e = None
@@ -365,7 +372,8 @@ def run_ours(args, cfg, rank, local, world):
                      "traffic": ncu_traffic(kname), "algorithmic_bytes_per_launch": bytes_decode, "peak_source": peak_src,
                      "contraction": {"achieved": bytes_gemm / (gemm_ms * 1e-3) / 1e9, "frac": bytes_gemm / (gemm_ms * 1e-3) / 1e9 / peak,
                                      "algorithmic_bytes_per_launch": bytes_gemm, "traffic": ncu_traffic("contraction")}},
-        "check": {"mean_iou": float(scores["Mean IoU"]), "pixels_scored": total_px},
+        "check": {"mean_iou": float(scores["Mean IoU"]), "pixels_scored": total_px, "max_logit_err_vs_fp32_kernel": logit_err,
+                  "labels_differing_from_generic_kernel": label_mismatch},
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = time_cpu_baseline(cfg, min(cfg["B"], 64 if cfg["Q"] <= 128 else 2), 3, args.iid)

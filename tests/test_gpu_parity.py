@@ -82,6 +82,21 @@ def test_tcgen05_path_is_taken_and_matches_fp32_kernel(zb):
             assert float((ff.double() - ref).abs().max()) / scale <= 2e-6
         one = zb.ops.contraction(text, tok, precision="tf32")
         assert 1e-5 < float((one.double() - ref).abs().max()) / scale <= 2e-2
+    # more tiles than CTAs: every CTA runs several tiles back to back with all rings full (24*13 = 312 tiles on
+    # 148 SMs).  A slot-reuse race in the pipeline only shows up here, so check EVERY image.
+    text = torch.nn.functional.normalize(torch.randn(81, 512, generator=gen), dim=-1).cuda()
+    tok = torch.nn.functional.normalize(torch.randn(24, 40, 40, 512, generator=gen), dim=-1).cuda()
+    ref = torch.einsum("nc,bhwc->bnhw", text.double(), tok.double())
+    for _ in range(3):
+        for prec in ("tf32x3", "tf32"):
+            got = zb.ops.contraction(text, tok, precision=prec)
+            per_image = (got.double() - ref).abs().amax(dim=(1, 2, 3)) / float(ref.abs().max())
+            assert float(per_image.max()) <= (1e-5 if prec == "tf32x3" else 2e-2), per_image.tolist()
+    wide = torch.nn.functional.normalize(torch.randn(920, 512, generator=gen), dim=-1).cuda()
+    tokw = torch.nn.functional.normalize(torch.randn(6, 56, 56, 512, generator=gen), dim=-1).cuda()      # 6*25*4 = 600 tiles
+    refw = torch.einsum("nc,bhwc->bnhw", wide.double(), tokw.double())
+    gotw = zb.ops.contraction(wide, tokw, precision="tf32x3")
+    assert float((gotw.double() - refw).abs().amax() / refw.abs().max()) <= 1e-5
     # per-image A operand (queries) with the fused sigmoid epilogue
     q = torch.nn.functional.normalize(torch.randn(3, 100, 768, generator=gen), dim=-1).cuda()
     feats = torch.randn(3, 15, 20, 768, generator=gen).cuda()

@@ -22,9 +22,8 @@
 // Warp roles (512 threads, 1 CTA / SM, persistent over tiles) and the three decoupled rings they run:
 //   warp 0      pixel-tile TMA producer   A ring  (smem, SA slots of 16 KB):  waits a_free[i]  -> arms a_full[i]
 //   warp 3      category TMA producer     B ring  (smem, SB slots hi|lo):    waits b_free[j]  -> arms b_full[j]
-//   warps 8-15  converters                A ring -> T ring: wait a_full[i], t_free[k]; ld.shared; arrive a_free[i]
-//                                         (the smem slot is free as soon as the row sits in registers); split;
-//                                         tcgen05.st; arrive t_ready[k]
+//   warps 8-15  converters                A ring -> T ring: wait a_full[i]; ld.shared; split; wait t_free[k];
+//                                         tcgen05.st; arrive t_ready[k], then a_free[i]
 //   warp 1      MMA issuer (one lane)     waits t_ready[k], b_full[j], tmem_empty[a]; 3 MMAs per k-step;
 //                                         commits t_free[k], b_free[j], and tmem_full[a] after the last slab
 //   warp 2      TMEM allocator / deallocator
@@ -429,7 +428,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
                     hi[e] = to_tf32_rn_fast(x[e]);
                     lo[e] = to_tf32_rn_fast(__fsub_rn(x[e], __uint_as_float(hi[e])));
                 }
-                mbar_arrive(bar_a_free(i));             // the row is in registers: the smem slot can be refilled
+                const int i_prev = i;
                 if (++i == p.sa) { i = 0; phi ^= 1; }
                 mbar_wait(bar_t_free(k), phk ^ 1);
                 tc_fence_after();
@@ -439,6 +438,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(bar_t_ready(k));
+                // Release the smem slot only now: this arrive is ordered after the tcgen05.st of the values loaded
+                // from the slot.  Arriving right after the ld.shared (no register dependence on the loads) let the
+                // barrier unit overtake the load unit; the next TMA then overwrote rows that were still being read
+                // (seen as wrong pixel rows, but only on a CTA's 2nd+ tile, when the rings run full).
+                mbar_arrive(bar_a_free(i_prev));
                 if (++k == p.st) { k = 0; phk ^= 1; }
             }
         }

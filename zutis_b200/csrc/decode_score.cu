@@ -146,6 +146,28 @@ __device__ __forceinline__ void tile_rows_argmax(const float* __restrict__ ra, c
     }
 }
 
+// Packed fp32x2 arithmetic (sm_100 FMUL2 / FFMA2): two IEEE round-to-nearest operations per issued instruction,
+// bit-identical to the scalar __fmul_rn / __fmaf_rn they replace.  The decode kernel is issue-bound, so halving the
+// FMA-pipe instruction count of the interpolation is worth ~1.5x on the main loop.
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 // chunked max tracking: `grp[r]` = index (in units of 4 categories, counted from category 0) of the
 // first group whose maximum is the running maximum of row r
 template <int NR>
@@ -157,19 +179,21 @@ __device__ __forceinline__ void tile_rows_groupmax(const float* __restrict__ ra,
     const float4* pb = reinterpret_cast<const float4*>(rb);
     const float4* pc = reinterpret_cast<const float4*>(ra + row_stride);
     const float4* pd = reinterpret_cast<const float4*>(rb + row_stride);
+    const unsigned long long LX0 = pack2(lx0, lx0), LX1 = pack2(lx1, lx1);
 #pragma unroll 2
     for (int g = 0; g < ngroups; ++g) {
         const float4 a = pa[g], b = pb[g], c = pc[g], d = pd[g];
-        const float t0 = lerp_w(lx0, a.x, lx1, b.x), t1 = lerp_w(lx0, a.y, lx1, b.y);
-        const float t2 = lerp_w(lx0, a.z, lx1, b.z), t3 = lerp_w(lx0, a.w, lx1, b.w);
-        const float u0 = lerp_w(lx0, c.x, lx1, d.x), u1 = lerp_w(lx0, c.y, lx1, d.y);
-        const float u2 = lerp_w(lx0, c.z, lx1, d.z), u3 = lerp_w(lx0, c.w, lx1, d.w);
+        // t = fma(lx0, a, lx1*b), u = fma(lx0, c, lx1*d) for the 4 categories of the group, two per instruction
+        const unsigned long long t01 = fma2(LX0, pack2(a.x, a.y), mul2(LX1, pack2(b.x, b.y)));
+        const unsigned long long t23 = fma2(LX0, pack2(a.z, a.w), mul2(LX1, pack2(b.z, b.w)));
+        const unsigned long long u01 = fma2(LX0, pack2(c.x, c.y), mul2(LX1, pack2(d.x, d.y)));
+        const unsigned long long u23 = fma2(LX0, pack2(c.z, c.w), mul2(LX1, pack2(d.z, d.w)));
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-            const float v0 = __fmaf_rn(ly0[r], t0, __fmul_rn(ly1[r], u0));
-            const float v1 = __fmaf_rn(ly0[r], t1, __fmul_rn(ly1[r], u1));
-            const float v2 = __fmaf_rn(ly0[r], t2, __fmul_rn(ly1[r], u2));
-            const float v3 = __fmaf_rn(ly0[r], t3, __fmul_rn(ly1[r], u3));
+            const unsigned long long LY0 = pack2(ly0[r], ly0[r]), LY1 = pack2(ly1[r], ly1[r]);
+            float v0, v1, v2, v3;
+            unpack2(fma2(LY0, t01, mul2(LY1, u01)), v0, v1);      // v = fma(ly0, t, ly1*u)
+            unpack2(fma2(LY0, t23, mul2(LY1, u23)), v2, v3);
             const float m = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
             if (m > best[r]) { best[r] = m; grp[r] = g0 + g; }
         }

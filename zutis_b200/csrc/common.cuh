@@ -19,6 +19,10 @@ int check_launch(const char* what);
 int sm_count();            // SMs of the current device (cached per device)
 int current_device_ok();   // ZUTIS_OK iff current device is sm_100
 
+// decode_score.cu: tiled interp(probabilities) > threshold kernel; ZUTIS_ERR_UNSUPPORTED => use the generic kernel
+int launch_threshold_tiled(const float* probs, long sb, long sq, long sy, long sx, int B, int Q, int h, int w, int H, int W,
+                           float threshold, uint32_t* bits, int* areas, cudaStream_t stream);
+
 #define ZUTIS_REQUIRE(cond, ...)                                   \
     do {                                                           \
         if (!(cond)) return ::zutis::fail(ZUTIS_ERR_BAD_ARG, __VA_ARGS__); \

@@ -479,6 +479,212 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const
     }
 }
 
+
+// ------------------------------------------------------------------------- tiled threshold kernel
+// interp(probabilities) > threshold -> bit-packed masks (networks/zutis.py:422-425).  Same work decomposition and
+// tap staging as decode_tiled_kernel (warp = 32 output columns x <= 8 rows of one cell row, double-buffered
+// cp.async tiles); per 4 queries and row the four comparisons are turned into four 32-pixel words by warp ballots,
+// lane (4*row + j) keeps word (row, query 4g+j) and the warp issues ONE 32-address store per group of 4 queries.
+struct ThresholdParams {
+    const float* probs;
+    long sb, sq, sy, sx;
+    int B, Q, h, w, H, W;
+    float scale_y, scale_x, threshold;
+    uint32_t* bits;      // [B,Q,H,words]
+    int* areas;          // [B,Q] or null
+    int words, XB, XR, QC, QS, n_groups, vec_stage;
+    long n_items;
+};
+
+__global__ void __launch_bounds__(kTiledWarps * 32, 2) threshold_tiled_kernel(const ThresholdParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    int* s_ystart = reinterpret_cast<int*>(smem);                                // [h+1]
+    int4* s_groups = reinterpret_cast<int4*>(s_ystart + ((p.h + 1 + 3) & ~3));   // [n_groups]: cy, Y0, nrows
+    float2* s_ly = reinterpret_cast<float2*>(s_groups + p.n_groups);             // [H]: (ly0, ly1)
+    const int row_stride = p.XR * p.QS;
+    const int tile_floats = 2 * row_stride;
+    float* tiles = reinterpret_cast<float*>(s_ly + ((p.H + 1) & ~1)) + warp * (2 * tile_floats);
+
+    for (int cy = threadIdx.x; cy <= p.h; cy += blockDim.x) s_ystart[cy] = first_dst_with_tap_ge(cy, p.h, p.H, p.scale_y);
+    for (int Y = threadIdx.x; Y < p.H; Y += blockDim.x) {
+        const AxisTap ty = axis_tap(Y, p.h, p.H, p.scale_y);
+        s_ly[Y] = make_float2(ty.l0, ty.l1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int g = 0;
+        for (int cy = 0; cy < p.h; ++cy)
+            for (int y = s_ystart[cy]; y < s_ystart[cy + 1] && g < p.n_groups; y += 8)
+                s_groups[g++] = make_int4(cy, y, min(8, s_ystart[cy + 1] - y), 0);
+        for (; g < p.n_groups; ++g) s_groups[g] = make_int4(0, 0, 0, 0);
+    }
+    __syncthreads();
+
+    const int nchunk = (p.Q + p.QC - 1) / p.QC;
+    const unsigned n_units_total = (unsigned)p.n_items * nchunk;      // chunks are independent here: any warp may take any unit
+    const unsigned first = blockIdx.x * kTiledWarps + warp;
+    const unsigned stride = gridDim.x * kTiledWarps;
+    const int sx = (int)p.sx, sy = (int)p.sy, sq = (int)p.sq;
+
+    auto decode_unit = [&](unsigned u) {
+        Unit un;
+        un.ch = (int)(u % (unsigned)nchunk);
+        const unsigned item = u / (unsigned)nchunk;
+        un.xb = (int)(item % (unsigned)p.XB);
+        const unsigned t = item / (unsigned)p.XB;
+        const int4 grp = s_groups[t % (unsigned)p.n_groups];
+        un.b = (int)(t / (unsigned)p.n_groups);
+        un.cy = grp.x; un.Y0 = grp.y; un.nr = grp.z;
+        un.rx_lo = axis_tap(un.xb * 32, p.w, p.W, p.scale_x).i0;
+        return un;
+    };
+    auto stage = [&](const Unit& un, float* tile) {
+        const int cy1 = un.cy + (un.cy < p.h - 1 ? 1 : 0);
+        const int q0 = un.ch * p.QC;
+        const int qc = min(p.QC, p.Q - q0);
+        const float* img = p.probs + (long)un.b * p.sb + (long)q0 * p.sq;
+        const int off0 = un.cy * sy, off1 = cy1 * sy;
+        if (p.vec_stage) {
+            const int cpp = (qc + 3) >> 2;
+            const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(tile) + (uint32_t)lane * 16u;
+            if (lane < cpp) {
+                for (int rx = 0; rx < p.XR; ++rx) {
+                    const int gx = min(un.rx_lo + rx, p.w - 1) * sx + lane * 4;
+                    cp_async16(tbase + (uint32_t)(rx * p.QS) * 4u, img + off0 + gx);
+                    cp_async16(tbase + (uint32_t)((p.XR + rx) * p.QS) * 4u, img + off1 + gx);
+                }
+            }
+        } else {
+            for (int rx = 0; rx < p.XR; ++rx) {
+                const int gx = min(un.rx_lo + rx, p.w - 1) * sx;
+                for (int j = lane; j < ((qc + 3) & ~3); j += 32) {
+                    tile[rx * p.QS + j] = j < qc ? __ldg(img + off0 + gx + j * sq) : 0.0f;
+                    tile[(p.XR + rx) * p.QS + j] = j < qc ? __ldg(img + off1 + gx + j * sq) : 0.0f;
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    int buf = 0;
+    Unit cur;
+    if (first < n_units_total) { cur = decode_unit(first); stage(cur, tiles); }
+    const int my_row = lane >> 2, my_j = lane & 3;            // the (row, query-in-group) whose word this lane keeps
+
+    for (unsigned u = first; u < n_units_total; u += stride, buf ^= 1) {
+        float* tile = tiles + buf * tile_floats;
+        const Unit un = cur;
+        const int q0 = un.ch * p.QC;
+        const int qc = min(p.QC, p.Q - q0);
+        const int ngroups = (qc + 3) >> 2;
+        const int X = un.xb * 32 + lane;
+        const bool xvalid = X < p.W;
+        const AxisTap tx = axis_tap(xvalid ? X : p.W - 1, p.w, p.W, p.scale_x);
+        cp_async_wait_all();
+        __syncwarp();
+        if (u + stride < n_units_total) { cur = decode_unit(u + stride); stage(cur, tiles + (buf ^ 1) * tile_floats); }
+
+        unsigned long long LY0[8], LY1[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const float2 l = s_ly[min(un.Y0 + r, p.H - 1)];
+            LY0[r] = pack2(l.x, l.x); LY1[r] = pack2(l.y, l.y);
+        }
+        const unsigned long long LX0 = pack2(tx.l0, tx.l0), LX1 = pack2(tx.l1, tx.l1);
+        const float4* pa = reinterpret_cast<const float4*>(tile + (tx.i0 - un.rx_lo) * p.QS);
+        const float4* pb = reinterpret_cast<const float4*>(tile + (tx.i1 - un.rx_lo) * p.QS);
+        const float4* pc = reinterpret_cast<const float4*>(tile + (tx.i0 - un.rx_lo) * p.QS + row_stride);
+        const float4* pd = reinterpret_cast<const float4*>(tile + (tx.i1 - un.rx_lo) * p.QS + row_stride);
+        const float thr = p.threshold;
+        // word (row my_row, query q0 + 4g + my_j) goes to bits[((b*Q + q)*H + Y)*words + xb]
+        const bool row_ok = my_row < un.nr;
+        uint32_t* out = p.bits + (((size_t)un.b * p.Q + q0 + my_j) * p.H + un.Y0 + my_row) * p.words + un.xb;
+        const size_t q_step = (size_t)4 * p.H * p.words;
+#pragma unroll 1
+        for (int g = 0; g < ngroups; ++g) {
+            const float4 a = pa[g], b = pb[g], c = pc[g], d = pd[g];
+            const unsigned long long t01 = fma2(LX0, pack2(a.x, a.y), mul2(LX1, pack2(b.x, b.y)));
+            const unsigned long long t23 = fma2(LX0, pack2(a.z, a.w), mul2(LX1, pack2(b.z, b.w)));
+            const unsigned long long u01 = fma2(LX0, pack2(c.x, c.y), mul2(LX1, pack2(d.x, d.y)));
+            const unsigned long long u23 = fma2(LX0, pack2(c.z, c.w), mul2(LX1, pack2(d.z, d.w)));
+            unsigned mine = 0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                float v0, v1, v2, v3;
+                unpack2(fma2(LY0[r], t01, mul2(LY1[r], u01)), v0, v1);
+                unpack2(fma2(LY0[r], t23, mul2(LY1[r], u23)), v2, v3);
+                const unsigned w0 = __ballot_sync(0xffffffffu, xvalid && v0 > thr);
+                const unsigned w1 = __ballot_sync(0xffffffffu, xvalid && v1 > thr);
+                const unsigned w2 = __ballot_sync(0xffffffffu, xvalid && v2 > thr);
+                const unsigned w3 = __ballot_sync(0xffffffffu, xvalid && v3 > thr);
+                if (my_row == r) mine = my_j == 0 ? w0 : (my_j == 1 ? w1 : (my_j == 2 ? w2 : w3));
+            }
+            const bool q_ok = 4 * g + my_j < qc;
+            if (row_ok && q_ok) out[(size_t)g * q_step] = mine;
+            if (p.areas) {
+                int cnt = (row_ok && q_ok) ? __popc(mine) : 0;
+                cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
+                cnt += __shfl_xor_sync(0xffffffffu, cnt, 8);
+                cnt += __shfl_xor_sync(0xffffffffu, cnt, 16);
+                if (lane < 4 && q_ok && cnt) atomicAdd(p.areas + (size_t)un.b * p.Q + q0 + 4 * g + lane, cnt);
+            }
+        }
+    }
+    cp_async_wait_all();
+}
+
+// Host side of the tiled threshold kernel; returns ZUTIS_ERR_UNSUPPORTED when the shape needs the generic kernel.
+int launch_threshold_tiled(const float* probs, long sb, long sq, long sy, long sx, int B, int Q, int h, int w, int H, int W,
+                           float threshold, uint32_t* bits, int* areas, cudaStream_t stream) {
+    if (H < h || W < w || (H == h && W == w)) return ZUTIS_ERR_UNSUPPORTED;
+    ThresholdParams p;
+    p.probs = probs; p.sb = sb; p.sq = sq; p.sy = sy; p.sx = sx;
+    p.B = B; p.Q = Q; p.h = h; p.w = w; p.H = H; p.W = W;
+    p.scale_y = axis_scale(h, H); p.scale_x = axis_scale(w, W); p.threshold = threshold;
+    p.bits = bits; p.areas = areas; p.words = (W + 31) / 32; p.XB = p.words;
+    int XR = 0;
+    for (int xb = 0; xb < p.XB; ++xb) {
+        const int lo = axis_tap(xb * 32, w, W, p.scale_x).i0;
+        const int last = (xb * 32 + 31 < W) ? xb * 32 + 31 : W - 1;
+        const int hi = axis_tap(last, w, W, p.scale_x).i1;
+        if (hi - lo + 1 > XR) XR = hi - lo + 1;
+    }
+    if (XR > 8) return ZUTIS_ERR_UNSUPPORTED;
+    p.XR = XR;
+    p.QC = Q <= 128 ? ((Q + 3) & ~3) : 128;
+    p.QS = p.QC;
+    while ((p.QS & 7) != 4) p.QS += 4;
+    int groups = 0, prev = 0;
+    for (int cy = 0; cy < h; ++cy) {
+        int lo = prev, hi = H;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (axis_tap(mid, h, H, p.scale_y).i0 >= cy + 1) hi = mid; else lo = mid + 1; }
+        groups += (lo - prev + 7) / 8;
+        prev = lo;
+    }
+    p.n_groups = groups;
+    p.n_items = (long)B * groups * p.XB;
+    p.vec_stage = (sq == 1) && ((sx & 3) == 0) && ((sy & 3) == 0) && ((sb & 3) == 0) && (sx >= ((Q + 3) & ~3)) &&
+                  ((reinterpret_cast<uintptr_t>(probs) & 15) == 0);
+    const int nchunk = (Q + p.QC - 1) / p.QC;
+    const size_t smem = (size_t)((h + 1 + 3) & ~3) * 4 + (size_t)groups * 16 + (size_t)((H + 1) & ~1) * 8 +
+                        (size_t)kTiledWarps * 2 * 2 * XR * p.QS * 4;
+    const long extent = (long)(h - 1) * sy + (long)(w - 1) * sx + (long)(Q - 1) * sq;
+    if (groups > kMaxGroups || H > kMaxTableRows || smem > 200 * 1024 || extent >= 2147483647L || sx < 0 || sy < 0 || sq < 0 ||
+        p.n_items * nchunk >= 2147483647L)
+        return ZUTIS_ERR_UNSUPPORTED;
+    ZUTIS_CUDA(cudaFuncSetAttribute(threshold_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    ZUTIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, threshold_tiled_kernel, kTiledWarps * 32, smem));
+    if (per_sm < 1) return ZUTIS_ERR_UNSUPPORTED;
+    long blocks = (p.n_items * nchunk + kTiledWarps - 1) / kTiledWarps;
+    const long cap = (long)sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
+    threshold_tiled_kernel<<<(unsigned)blocks, kTiledWarps * 32, smem, stream>>>(p);
+    return check_launch("threshold_tiled_kernel");
+}
+
 }  // namespace zutis
 
 using namespace zutis;

@@ -4,6 +4,7 @@
 //   unpack_bits_kernel      bit-packed -> one byte per pixel for legacy consumers
 //   pair_inter_kernel       popcount(mask_i & mask_j): the counts behind compute_iou  utils/iou.py:31-33 (NMS, zutis.py:258-259)
 //   lowres_stats_kernel     mask sizes, in-mask probability sums, masked mean tokens  networks/zutis.py:390-406
+//   (the tiled threshold kernel lives in decode_score.cu next to the decode kernel whose staging it shares)
 //   categories_kernel       sigmoid(T * cos(text, mean token)) -> argmax / max        networks/zutis.py:409-420
 // Compiled with -fmad=false; interpolation uses the same explicit fma pattern as decode_score.cu.
 #include "common.cuh"
@@ -95,70 +96,139 @@ __global__ void __launch_bounds__(256) pair_inter_kernel(const uint32_t* bits, i
     }
 }
 
-// block per (b,q): size, probability sum and masked mean token.  Deterministic: fixed-order tree for the
-// scalar sums, ascending-pixel accumulation per channel for the token sum.
+// Low-resolution instance statistics (networks/zutis.py:390-406).  One block per (image, tile of kStatQ queries,
+// slice of kStatD channels):
+//   phase 1  threads sweep the h*w probabilities of the tile's queries once: per pixel a 16-bit word of ">" bits goes
+//            to shared memory, per query the mask size and the in-mask probability sum are block-reduced (fixed tree);
+//   phase 2  the image's tokens are streamed once per query TILE (not once per query): thread = one channel and one
+//            of 4 pixel phases, the token value is added to the accumulators of the queries whose bit is set; the 4
+//            phases are then combined in a fixed order (deterministic).
+// The reference materialises this as a [B,100,h,w,512] broadcast (0.98 GB per image).
+constexpr int kStatQ = 16;
+constexpr int kStatD = 64;
+
 __global__ void __launch_bounds__(256) lowres_stats_kernel(const float* probs, long sb, long sq, long sy, long sx,
                                                            const float* tokens, int Q, int h, int w, int D, float threshold,
                                                            int* sizes, float* psum, float* mean_tokens) {
-    extern __shared__ unsigned char s_mask[];      // [h*w] flags, then reduction scratch
-    const int bq = blockIdx.x;
-    const int b = bq / Q, q = bq % Q;
+    extern __shared__ unsigned short s_bits[];     // [h*w] one bit per query of the tile
+    __shared__ int r_cnt[8][kStatQ];
+    __shared__ float r_sum[8][kStatQ];
+    __shared__ float s_denom[kStatQ];
+    __shared__ float s_part[3][kStatQ][kStatD];    // partial sums of pixel phases 1..3
+    const int tiles_per_image = (Q + kStatQ - 1) / kStatQ;
+    const int b = blockIdx.x / tiles_per_image;
+    const int q0 = (blockIdx.x % tiles_per_image) * kStatQ;
+    const int nq = min(kStatQ, Q - q0);
     const int hw = h * w;
-    const float* plane = probs + (long)b * sb + (long)q * sq;
-    int cnt = 0;
-    float sum = 0.0f;
-    for (int i = threadIdx.x; i < hw; i += blockDim.x) {
-        const float v = plane[(long)(i / w) * sy + (long)(i % w) * sx];
-        const bool on = v > threshold;
-        s_mask[i] = on;
-        if (on) { ++cnt; sum = __fadd_rn(sum, v); }
+    const float* img = probs + (long)b * sb + (long)q0 * sq;
+    {
+        int cnt[kStatQ];
+        float sum[kStatQ];
+#pragma unroll
+        for (int j = 0; j < kStatQ; ++j) { cnt[j] = 0; sum[j] = 0.0f; }
+        for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+            const float* px = img + (long)(i / w) * sy + (long)(i % w) * sx;
+            unsigned bits = 0;
+#pragma unroll
+            for (int j = 0; j < kStatQ; ++j) {
+                if (j < nq) {
+                    const float v = px[(long)j * sq];
+                    if (v > threshold) { bits |= 1u << j; ++cnt[j]; sum[j] = __fadd_rn(sum[j], v); }
+                }
+            }
+            s_bits[i] = (unsigned short)bits;
+        }
+#pragma unroll
+        for (int j = 0; j < kStatQ; ++j) {
+            for (int o = 16; o > 0; o >>= 1) {
+                cnt[j] += __shfl_xor_sync(0xffffffffu, cnt[j], o);
+                sum[j] = __fadd_rn(sum[j], __shfl_xor_sync(0xffffffffu, sum[j], o));
+            }
+            if ((threadIdx.x & 31) == 0) { r_cnt[threadIdx.x >> 5][j] = cnt[j]; r_sum[threadIdx.x >> 5][j] = sum[j]; }
+        }
     }
-    __shared__ int r_cnt[8];
-    __shared__ float r_sum[8];
-    for (int o = 16; o > 0; o >>= 1) {
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
-    }
-    if ((threadIdx.x & 31) == 0) { r_cnt[threadIdx.x >> 5] = cnt; r_sum[threadIdx.x >> 5] = sum; }
     __syncthreads();
-    int total = 0;
-    float tsum = 0.0f;
-    for (int k = 0; k < 8; ++k) { total += r_cnt[k]; tsum = __fadd_rn(tsum, r_sum[k]); }
-    if (threadIdx.x == 0) { sizes[bq] = total; psum[bq] = tsum; }
-    if (mean_tokens) {
-        const float denom = __fadd_rn((float)total, 1e-7f);      // (mask_sizes + 1e-7) promotes to fp32, zutis.py:406
-        const float* tok = tokens + (long)b * hw * D;
-        for (int d = threadIdx.x; d < D; d += blockDim.x) {
-            float acc = 0.0f;
-            for (int i = 0; i < hw; ++i)
-                if (s_mask[i]) acc = __fadd_rn(acc, tok[(long)i * D + d]);
-            mean_tokens[(long)bq * D + d] = acc / denom;
+    if (threadIdx.x < nq) {
+        int total = 0;
+        float tsum = 0.0f;
+        for (int k = 0; k < 8; ++k) { total += r_cnt[k][threadIdx.x]; tsum = __fadd_rn(tsum, r_sum[k][threadIdx.x]); }
+        if (blockIdx.y == 0) {
+            sizes[(long)b * Q + q0 + threadIdx.x] = total;
+            psum[(long)b * Q + q0 + threadIdx.x] = tsum;
+        }
+        s_denom[threadIdx.x] = __fadd_rn((float)total, 1e-7f);    // (mask_sizes + 1e-7) promotes to fp32, zutis.py:406
+    }
+    __syncthreads();
+    if (!mean_tokens) return;
+    const int c = threadIdx.x & (kStatD - 1);      // channel within the slice
+    const int phase = threadIdx.x / kStatD;        // 0..3: pixels i = phase, phase+4, ...
+    const int d = blockIdx.y * kStatD + c;
+    const float* tok = tokens + (long)b * hw * D + d;
+    float acc[kStatQ];
+#pragma unroll
+    for (int j = 0; j < kStatQ; ++j) acc[j] = 0.0f;
+    if (d < D) {
+        // batches of 8 pixels: all token loads of a batch are issued before any is consumed (the loop is otherwise
+        // one exposed global-load latency per pixel)
+        for (int i0 = phase; i0 < hw; i0 += 32) {
+            float v[8];
+            unsigned bits[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = i0 + 4 * k;
+                bits[k] = i < hw ? s_bits[i] : 0u;
+                v[k] = bits[k] ? __ldg(tok + (long)i * D) : 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (bits[k] == 0) continue;                      // warp-uniform: a warp shares its pixel phase
+#pragma unroll
+                for (int j = 0; j < kStatQ; ++j)
+                    if (bits[k] & (1u << j)) acc[j] = __fadd_rn(acc[j], v[k]);
+            }
+        }
+    }
+    if (phase > 0) {
+#pragma unroll
+        for (int j = 0; j < kStatQ; ++j) s_part[phase - 1][j][c] = acc[j];
+    }
+    __syncthreads();
+    if (phase == 0 && d < D) {
+#pragma unroll
+        for (int j = 0; j < kStatQ; ++j) {
+            if (j < nq) {
+                const float total = __fadd_rn(__fadd_rn(acc[j], s_part[0][j][c]), __fadd_rn(s_part[1][j][c], s_part[2][j][c]));
+                mean_tokens[((long)b * Q + q0 + j) * D + d] = total / s_denom[j];
+            }
         }
     }
 }
 
-// block per (b,q): cosine of the mean token with every text row, sigmoid(T*cos), first-max category.
+// block per (b,q): cosine of the mean token with every text row, sigmoid(T*cos), first-max category
+// (networks/zutis.py:409-420).  A warp takes one category at a time: lanes stride the channel dimension (coalesced
+// reads of the text row), partial sums are combined by a shuffle tree.
 __global__ void __launch_bounds__(128) categories_kernel(const float* mean_tokens, const float* text, int n_cat, int D,
                                                          float temperature, int* category, float* max_prob) {
     extern __shared__ float s_tok[];               // [D] normalised token, then [n_cat] probabilities
     float* s_prob = s_tok + D;
     const int bq = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* t = mean_tokens + (long)bq * D;
     float ss = 0.0f;
     for (int d = threadIdx.x; d < D; d += blockDim.x) { const float v = t[d]; s_tok[d] = v; ss = __fmaf_rn(v, v, ss); }
     __shared__ float red[4];
     for (int o = 16; o > 0; o >>= 1) ss = __fadd_rn(ss, __shfl_xor_sync(0xffffffffu, ss, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    if (lane == 0) red[warp] = ss;
     __syncthreads();
     const float norm = __fadd_rn(sqrtf(__fadd_rn(__fadd_rn(red[0], red[1]), __fadd_rn(red[2], red[3]))), 1e-7f);   // zutis.py:412
     for (int d = threadIdx.x; d < D; d += blockDim.x) s_tok[d] = s_tok[d] / norm;
     __syncthreads();
-    for (int n = threadIdx.x; n < n_cat; n += blockDim.x) {
+    for (int n = warp; n < n_cat; n += 4) {
         const float* e = text + (long)n * D;
         float acc = 0.0f;
-        for (int d = 0; d < D; ++d) acc = __fmaf_rn(e[d], s_tok[d], acc);
-        const float z = __fmul_rn(acc, temperature);
-        s_prob[n] = 1.0f / (1.0f + expf(-z));
+        for (int d = lane; d < D; d += 32) acc = __fmaf_rn(__ldg(e + d), s_tok[d], acc);
+        for (int o = 16; o > 0; o >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+        if (lane == 0) s_prob[n] = 1.0f / (1.0f + expf(-__fmul_rn(acc, temperature)));
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -212,6 +282,11 @@ extern "C" int zutis_decode_threshold(const float* probs, long sb, long sq, long
     int st = make_plane_params(&p, probs, sb, sq, sy, sx, B, Q, h, w, H, W, "zutis_decode_threshold");
     if (st != ZUTIS_OK) return st;
     ZUTIS_REQUIRE(mask_bits != nullptr, "zutis_decode_threshold: mask_bits is NULL");
+    {
+        // fast path: warp-tile kernel with staged taps (up-sampling by >= ~5x); anything else takes the generic kernel
+        const int tiled = launch_threshold_tiled(probs, sb, sq, sy, sx, B, Q, h, w, H, W, threshold, mask_bits, areas, (cudaStream_t)stream);
+        if (tiled != ZUTIS_ERR_UNSUPPORTED) return tiled;
+    }
     const long nwords = (long)B * Q * H * ((W + 31) / 32);
     threshold_kernel<<<grid_for(nwords, 8), 256, 0, (cudaStream_t)stream>>>(p, threshold, mask_bits, areas);
     return check_launch("threshold_kernel");
@@ -247,12 +322,13 @@ extern "C" int zutis_instance_lowres_stats(const float* probs, long sb, long sq,
     ZUTIS_REQUIRE(!mean_tokens || (tokens && D > 0), "zutis_instance_lowres_stats: mean_tokens needs tokens and D");
     int st = current_device_ok();
     if (st != ZUTIS_OK) return st;
-    const size_t smem = (size_t)h * w;
-    ZUTIS_REQUIRE(smem <= 200 * 1024, "zutis_instance_lowres_stats: h*w=%zu too large", smem);
+    const size_t smem = (size_t)h * w * 2;
+    ZUTIS_REQUIRE(smem <= 180 * 1024, "zutis_instance_lowres_stats: h*w=%d too large", h * w);
     if (smem > 48 * 1024)
         ZUTIS_CUDA(cudaFuncSetAttribute(lowres_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lowres_stats_kernel<<<(unsigned)(B * Q), 256, smem, (cudaStream_t)stream>>>(probs, sb, sq, sy, sx, tokens, Q, h, w, D, threshold,
-                                                                                 sizes, psum, mean_tokens);
+    const dim3 blocks((unsigned)(B * ((Q + kStatQ - 1) / kStatQ)), mean_tokens ? (unsigned)((D + kStatD - 1) / kStatD) : 1u);
+    lowres_stats_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(probs, sb, sq, sy, sx, tokens, Q, h, w, D, threshold,
+                                                                       sizes, psum, mean_tokens);
     return check_launch("lowres_stats_kernel");
 }
 

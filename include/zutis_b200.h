@@ -60,7 +60,10 @@ enum {
     ZUTIS_GEMM_TF32X3 = 1,         /* tcgen05 kind::tf32, 3-term error-compensated split (fp32-grade) */
     ZUTIS_GEMM_TF32 = 2,           /* tcgen05 kind::tf32, single pass (reduced precision: meets the 2e-2 logit bar only) */
     ZUTIS_GEMM_PRECISION_MASK = 3,
-    ZUTIS_GEMM_SIGMOID = 16        /* fused sigmoid epilogue (zutis.py:209) */
+    ZUTIS_GEMM_SIGMOID = 16,       /* fused sigmoid epilogue (zutis.py:209) */
+    ZUTIS_GEMM_A_PREPARED = 32     /* tcgen05 paths: `workspace` still holds the hi/lo split of this same A from an earlier
+                                      call with identical M, K, batch and flags (text embeddings are constant per model,
+                                      zutis.py:36-38), so the split kernel is skipped */
 };
 
 ZUTIS_API const char* zutis_last_error_string(void);

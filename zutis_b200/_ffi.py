@@ -19,6 +19,7 @@ GT_U8, GT_I16, GT_I32, GT_I64 = range(4)
 DECODE_AUTO, DECODE_GENERIC, DECODE_TILED, DECODE_PRUNED = range(4)
 GEMM_FP32_SIMT, GEMM_TF32X3, GEMM_TF32 = 0, 1, 2
 GEMM_SIGMOID = 16
+GEMM_A_PREPARED = 32
 
 
 class ZutisError(RuntimeError):

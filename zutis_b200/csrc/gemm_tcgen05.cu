@@ -552,9 +552,12 @@ int launch_gemm_tcgen05(const GemmParams& g, int batch, int flags, void* workspa
     const long split_elems = (long)images * pl.rows_per_image * g.K;
     long sblocks = (split_elems + 255) / 256;
     if (sblocks > (long)sms * 8) sblocks = (long)sms * 8;
-    split_operand_kernel<<<(unsigned)sblocks, 256, 0, stream>>>(g.A, g.lda, g.strideA, g.M, g.K, pl.rows_per_image, images, ws_hi, ws_lo);
-    int st = check_launch("split_operand_kernel");
-    if (st != ZUTIS_OK) return st;
+    int st = ZUTIS_OK;
+    if (!(flags & ZUTIS_GEMM_A_PREPARED)) {
+        split_operand_kernel<<<(unsigned)sblocks, 256, 0, stream>>>(g.A, g.lda, g.strideA, g.M, g.K, pl.rows_per_image, images, ws_hi, ws_lo);
+        st = check_launch("split_operand_kernel");
+        if (st != ZUTIS_OK) return st;
+    }
 
     CUtensorMap map_pix, map_hi, map_lo;
     st = make_map(&map_pix, g.Bm, (long)batch * g.N, g.K, g.ldb, BLOCK_M);

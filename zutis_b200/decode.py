@@ -132,7 +132,8 @@ def predict(
     text = self.text_embeddings
     if mask_type == "semantic":
         tokens = dict_outputs["patch_tokens"]                      # b x h x w x n_dims
-        lowres = ops.contraction(text.to(tokens.device), tokens, precision=precision)     # b x n x h x w
+        lowres = ops.contraction(text.to(tokens.device), tokens, precision=precision,
+                                 a_cache=self.__dict__.setdefault("_zutis_b200_text_cache", {}))       # b x n x h x w
         if return_logits:
             # the one mode in which full-resolution logits are materialised, on request (zutis.py:369-370)
             return ops.upsample_bilinear(lowres, size) if size is not None else lowres

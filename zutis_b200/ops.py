@@ -49,13 +49,15 @@ def gemm_flags(precision: Optional[str], sigmoid: bool = False) -> int:
 
 
 def contraction(a: torch.Tensor, feats: torch.Tensor, *, precision: Optional[str] = None, sigmoid: bool = False,
-                pixel_major: bool = True) -> torch.Tensor:
+                pixel_major: bool = True, a_cache: Optional[dict] = None) -> torch.Tensor:
     """out[b,n,y,x] = act(sum_c a[(b,)n,c] * feats[b,y,x,c])   (zutis.py:361-365, :184-186 + :209).
 
     a: [M,C] shared by the batch (text embeddings) or [B,M,C] per image (queries).
     feats: [B,h,w,C] channel-last.  Returns a [B,M,h,w] tensor; with ``pixel_major`` its memory
     is [B,h,w,Mp] (category index contiguous, Mp = M rounded up to 4) -- the layout the fused
     decode kernel streams -- otherwise it is a contiguous [B,M,h,w].
+    ``a_cache``: a dict owned by the caller; for a batch-shared ``a`` (text embeddings, constant per
+    model) the tensor-core kernel's prepared operand is kept there and reused by later calls.
     """
     _need_cuda(a, "a"); _need_cuda(feats, "feats")
     if feats.dim() != 4:
@@ -88,8 +90,18 @@ def contraction(a: torch.Tensor, feats: torch.Tensor, *, precision: Optional[str
         s_cn, s_cp, s_c = N, 1, M * N
         out = buf
     def launch(fl: int) -> None:
-        ws_bytes = F.lib().zutis_gemm_workspace_bytes(M, N, Cc, B, fl)
-        ws = torch.empty(ws_bytes, device=feats.device, dtype=torch.uint8) if ws_bytes else None
+        ws_bytes = F.lib().zutis_gemm_workspace_bytes(M, N, Cc, 1 if shared else B, fl)
+        ws = None
+        if ws_bytes and shared and a_cache is not None:
+            key = (a.data_ptr(), a._version, M, Cc, fl & F.GEMM_TF32X3 | fl & F.GEMM_TF32, str(feats.device))
+            ws = a_cache.get(key)
+            if ws is None:
+                a_cache.clear()
+                ws = a_cache[key] = torch.empty(ws_bytes, device=feats.device, dtype=torch.uint8)
+            else:
+                fl |= F.GEMM_A_PREPARED
+        elif ws_bytes:
+            ws = torch.empty(ws_bytes, device=feats.device, dtype=torch.uint8)
         with torch.cuda.device(feats.device):
             F.call("zutis_gemm_logits", a.data_ptr(), a.stride(-2), 0 if shared else a.stride(0),
                    feats.data_ptr(), feats.stride(2), feats.stride(0),

@@ -166,6 +166,20 @@ ZUTIS_API int zutis_instance_categories(const float* mean_tokens, long n_rows, c
                                         float temperature, int32_t* category, float* max_prob, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * SURVEY section 8(f) N1 -- the step right before the contraction: ZUTIS.image_to_text_space, ViT branch with
+ * channel_last=True                                                networks/zutis.py:319-322
+ *     y = einsum("bhwn,nc->bhwc", tokens, proj)   -> zutis_gemm_logits with A = proj^T (pixel-major output)
+ *     y = F.layer_norm(y, y.shape[1:])            -> statistics over ALL h*w*c elements of an image, eps 1e-5, no affine
+ *     y = y / (y.norm(dim=-1, keepdim=True) + 1e-7)
+ * This entry does the last two lines in place on x [B, pixels, D] (contiguous): per-image moments in a fixed-order
+ * two-stage reduction (deterministic), then one warp per pixel normalises its D channels.
+ * workspace: at least zutis_image_norm_workspace_bytes(B, pixels, D) bytes of device scratch.
+ * ------------------------------------------------------------------------------------------- */
+ZUTIS_API size_t zutis_image_norm_workspace_bytes(int B, long pixels, int D);
+ZUTIS_API int zutis_image_layernorm_l2norm(float* x, int B, long pixels, int D, int layer_norm, float ln_eps, float l2_eps,
+                                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * End-to-end entry with HOST buffers (what a caller holding numpy arrays uses; also bench.py's
  * `e2e` leg): text [Q,D], tokens [B,h,w,D] fp32 and gt [B,H,W] live in (ideally pinned) host memory;
  * the call copies them in, runs contraction -> fused decode+score -> merge, and returns the int64

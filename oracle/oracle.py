@@ -249,6 +249,17 @@ def torch_instance_masks(mask_proposals, size=None, threshold: float = 0.5) -> n
         return (mp > threshold).cpu().numpy()
 
 
+def torch_image_to_text_space(tokens, proj, layer_norm: bool = True):
+    """zutis.py:319-322 (ViT, channel_last=True): projection, joint layer norm over (h,w,c), per-pixel L2 norm."""
+    import torch
+    import torch.nn.functional as F
+    with torch.no_grad():
+        y = torch.einsum("bhwn,nc->bhwc", tokens, proj)
+        if layer_norm:
+            y = F.layer_norm(y, normalized_shape=y.shape[1:])
+        return y / (y.norm(dim=-1, keepdim=True) + 1e-7)
+
+
 def hard_nms(masks: np.ndarray, scores: np.ndarray, cats: np.ndarray,
              nms_threshold: float = 0.3, score_floor: float = 0.001) -> List[Tuple[int, int, float]]:
     """zutis.py:225-282 (nms_type="hard") -> list of (category, query index, score) kept.

@@ -210,6 +210,16 @@ def main():
             np.stack([np.ascontiguousarray(p["segmentation"]) for p in preds]).astype(bool).reshape(len(preds), -1), axis=1)
     ic["text"] = t.numpy(); ic["tokens"] = x.numpy(); ic["proposals"] = mp.numpy(); ic["size"] = np.array([70, 90])
     np.savez_compressed(os.path.join(OUT, "instance_cases.npz"), **ic)
+    # ------------------------------------------- 5. image_to_text_space (zutis.py:301-331)
+    ts = {}
+    gen = torch.Generator().manual_seed(13)
+    pt = torch.randn(2, 5, 6, 64, generator=gen) * 3 + 0.5
+    pj = torch.randn(64, 32, generator=gen) * 0.2
+    ns = SimpleNamespace(clip_arch="ViT-B/16")
+    ts["tokens"] = pt.numpy(); ts["proj"] = pj.numpy()
+    ts["out_ln"] = ZUTIS.image_to_text_space(ns, pt, pj, channel_last=True, layer_norm=True).numpy()
+    ts["out_noln"] = ZUTIS.image_to_text_space(ns, pt, pj, channel_last=True, layer_norm=False).numpy()
+    np.savez_compressed(os.path.join(OUT, "text_space.npz"), **ts)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

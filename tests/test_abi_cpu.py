@@ -44,7 +44,7 @@ def test_ctypes_table_matches_header():
 def test_argument_counts_match_header():
     text = open(os.path.join(ROOT, "include", "zutis_b200.h")).read()
     for name, (_, args) in _ffi.SIGNATURES.items():
-        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", text, re.S)
+        m = re.search(r"ZUTIS_API\s+[\w\s\*]+?\b" + name + r"\s*\(([^;]*?)\)\s*;", text, re.S)
         assert m, name
         params = m.group(1).strip()
         n = 0 if params in ("", "void") else params.count(",") + 1

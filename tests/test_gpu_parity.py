@@ -495,3 +495,24 @@ def test_host_entry_chunks_and_overlaps(zb):
     _ffi.call("zutis_semantic_eval_host", text.ctypes.data, tokens.ctypes.data, gt.ctypes.data, _ffi.GT_I32,
               B, Q, D, h, w, H, W, hist.ctypes.data, None, _ffi.GEMM_TF32X3, 0)          # accumulates into hist
     assert hist.sum() == 2 * B * (H - 3) * W
+
+
+def test_image_to_text_space_drop_in(zb, golden):
+    """projection + joint layer norm + per-pixel L2 norm (zutis.py:319-322)."""
+    g = golden("text_space")
+    dec = zb.ZutisDecoder(torch.zeros(2, 32).cuda())
+    dec.clip_arch = "ViT-B/16"
+    for key, ln in (("out_ln", True), ("out_noln", False)):
+        got = dec.image_to_text_space(dev(g["tokens"]), dev(g["proj"]), channel_last=True, layer_norm=ln)
+        assert tuple(got.shape) == g[key].shape and got.is_contiguous()
+        np.testing.assert_allclose(got.cpu().numpy(), g[key], rtol=0, atol=2e-6)
+    with pytest.raises(NotImplementedError):
+        dec.image_to_text_space(dev(g["tokens"]), dev(g["proj"]), channel_last=False)
+    # BASELINE cfg2 shape: 768 -> 512 projection of 64 x 40 x 40 tokens; unit rows, and the chain into the decoder
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    tok = torch.randn(8, 40, 40, 768, device="cuda", generator=gen)
+    proj = torch.randn(768, 512, device="cuda", generator=gen) * 0.03
+    got = dec.image_to_text_space(tok, proj, channel_last=True)
+    ref = O.torch_image_to_text_space(tok[:2].cpu(), proj.cpu())
+    np.testing.assert_allclose(got[:2].cpu().numpy(), ref.numpy(), rtol=0, atol=3e-6)
+    assert float((got.norm(dim=-1) - 1).abs().max()) < 1e-5

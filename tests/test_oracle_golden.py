@@ -152,3 +152,10 @@ def test_instance_decode_matches_reference(golden, fixture, prefix, tag):
     assert len(bits) == len(ref_bits)
     if bits:
         assert np.array_equal(np.stack(bits), ref_bits)
+
+
+def test_image_to_text_space_port_matches_reference(golden):
+    g = golden("text_space")
+    for key, ln in (("out_ln", True), ("out_noln", False)):
+        got = O.torch_image_to_text_space(torch.from_numpy(g["tokens"]), torch.from_numpy(g["proj"]), ln).numpy()
+        assert np.array_equal(got, g[key])

@@ -23,7 +23,7 @@ def __getattr__(name):
     lazy = {
         "RunningScore": "running_score", "compute_iou": "iou",
         "predict": "decode", "get_mask_proposals": "decode", "decode_and_score": "decode",
-        "ZutisDecoder": "decode", "install": "decode",
+        "ZutisDecoder": "decode", "install": "decode", "image_to_text_space": "decode",
         "shard_range": "distributed", "init_distributed": "distributed",
     }
     if name in lazy:

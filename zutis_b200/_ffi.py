@@ -56,6 +56,8 @@ SIGNATURES = {
     "zutis_pairwise_mask_intersections": (_i, [_vp, _i, _l, _vp, _vp]),
     "zutis_instance_lowres_stats": (_i, [_vp, _l, _l, _l, _l, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "zutis_instance_categories": (_i, [_vp, _l, _vp, _i, _i, _f, _vp, _vp, _vp]),
+    "zutis_image_norm_workspace_bytes": (_sz, [_i, _l, _i]),
+    "zutis_image_layernorm_l2norm": (_i, [_vp, _i, _l, _i, _i, _f, _f, _vp, _sz, _vp]),
     "zutis_semantic_eval_host": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i]),
 }
 

@@ -208,6 +208,28 @@ def get_mask_proposals(self, queries: torch.Tensor, patch_tokens: torch.Tensor, 
     return out.view(B, *lead, h, w)
 
 
+def image_to_text_space(self, patch_tokens: torch.Tensor, proj: torch.Tensor, channel_last: bool, layer_norm: bool = True,
+                        precision: Optional[str] = None) -> torch.Tensor:
+    """Same contract as ``ZUTIS.image_to_text_space`` (networks/zutis.py:301-331) for the branch ``forward`` uses with
+    a ViT encoder: ``channel_last=True`` -- projection ``einsum("bhwn,nc->bhwc")`` on the contraction kernel
+    (A = proj^T, pixel-major output = the [B,h,w,C] tensor itself), joint layer norm over (h,w,c) and per-pixel L2
+    normalisation in one fused pass.  SURVEY section 8(f) N1: the step right before the semantic contraction."""
+    if not channel_last or "RN" in getattr(self, "clip_arch", "ViT"):
+        raise NotImplementedError("zutis_b200.image_to_text_space covers the ViT / channel_last=True branch (zutis.py:319-322)")
+    cache = self.__dict__.setdefault("_zutis_b200_proj_cache", {})
+    key = (proj.data_ptr(), proj._version, tuple(proj.shape))
+    if cache.get("key") != key:
+        cache.clear(); cache["key"] = key
+        cache["projT"] = proj.detach().float().t().contiguous()            # [C, N]: rows are K-contiguous
+        cache["ws"] = {}
+    y = ops.contraction(cache["projT"], patch_tokens.detach(), precision=precision, a_cache=cache["ws"])   # view [B,C,h,w] over [B,h,w,Cp]
+    B, Cc, h, w = y.shape
+    buf = y.permute(0, 2, 3, 1)                                           # [B,h,w,C]
+    if not buf.is_contiguous():                                           # C not a multiple of 4: drop the padding columns
+        buf = buf.contiguous()
+    return ops.image_layernorm_l2norm_(buf, layer_norm=layer_norm)
+
+
 def decode_and_score(text: torch.Tensor, patch_tokens: torch.Tensor, label_trues, size, meter: RunningScore,
                      want_labels: bool = False, precision: Optional[str] = None):
     """Fused semantic evaluation step: contraction -> (upsample, argmax, confusion counts) on the device.
@@ -229,6 +251,7 @@ class ZutisDecoder:
 
     predict = predict
     get_mask_proposals = get_mask_proposals
+    image_to_text_space = image_to_text_space
 
     def decode_and_score(self, patch_tokens, label_trues, size, meter: RunningScore, want_labels: bool = False,
                          precision: Optional[str] = None):
@@ -239,3 +262,4 @@ def install(zutis_cls) -> None:
     """Bind the B200 decode path onto the reference model class (``networks.zutis.ZUTIS``)."""
     zutis_cls.predict = predict
     zutis_cls.get_mask_proposals = get_mask_proposals
+    zutis_cls.image_to_text_space = image_to_text_space

@@ -253,3 +253,17 @@ def instance_categories(mean_tokens: torch.Tensor, text: torch.Tensor, temperatu
         F.call("zutis_instance_categories", mean_tokens.contiguous().data_ptr(), B * Q, text.data_ptr(), text.shape[0], D,
                float(temperature), cat.data_ptr(), prob.data_ptr(), _stream())
     return cat, prob
+
+
+def image_layernorm_l2norm_(x: torch.Tensor, layer_norm: bool = True, ln_eps: float = 1e-5, l2_eps: float = 1e-7) -> torch.Tensor:
+    """In place on x [B,h,w,D] (contiguous fp32): joint layer norm over (h,w,D) then per-pixel L2 norm (zutis.py:321-322)."""
+    _need_cuda(x, "x")
+    if x.dim() != 4 or x.dtype != torch.float32 or not x.is_contiguous():
+        raise ValueError("x must be a contiguous fp32 [B,h,w,D] tensor")
+    B, h, w, D = x.shape
+    ws_bytes = F.lib().zutis_image_norm_workspace_bytes(B, h * w, D)
+    ws = torch.empty(max(ws_bytes, 8), device=x.device, dtype=torch.uint8)
+    with torch.cuda.device(x.device):
+        F.call("zutis_image_layernorm_l2norm", x.data_ptr(), B, h * w, D, int(layer_norm), float(ln_eps), float(l2_eps),
+               ws.data_ptr(), ws_bytes, _stream())
+    return x

@@ -168,6 +168,12 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
     return r;
 }
 
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 // chunked max tracking: `grp[r]` = index (in units of 4 categories, counted from category 0) of the
 // first group whose maximum is the running maximum of row r
 template <int NR>
@@ -194,8 +200,11 @@ __device__ __forceinline__ void tile_rows_groupmax(const float* __restrict__ ra,
             float v0, v1, v2, v3;
             unpack2(fma2(LY0, t01, mul2(LY1, u01)), v0, v1);      // v = fma(ly0, t, ly1*u)
             unpack2(fma2(LY0, t23, mul2(LY1, u23)), v2, v3);
-            const float m = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
-            if (m > best[r]) { best[r] = m; grp[r] = g0 + g; }
+            // running maximum folded into two 3-input max instructions; the group index moves only when the
+            // maximum moved (strictly greater, so the first group holding the maximum wins)
+            const float nb = max3(v2, v3, max3(v0, v1, best[r]));
+            if (nb != best[r]) grp[r] = g0 + g;
+            best[r] = nb;
         }
     }
 }

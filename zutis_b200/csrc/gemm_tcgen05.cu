@@ -48,7 +48,7 @@ constexpr int UMMA_K = 8;             // tf32 MMA K
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;     // 16 KB
 constexpr int NUM_THREADS = 512;
 constexpr int MAX_A = 8, MAX_B = 5, MAX_T = 5;   // ring depth limits
-constexpr int NUM_CONVERTERS = 256;   // threads
+constexpr int NUM_CONVERTER_WARPS = 8;
 constexpr int SMEM_LIMIT = 232448;    // 227 KB opt-in maximum per CTA
 
 struct TcParams {
@@ -249,10 +249,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_pix); prefetch_tmap(&map_cat_hi); prefetch_tmap(&map_cat_lo);
-        for (int i = 0; i < p.sa; ++i) { mbar_init(bar_a_full(i), 1); mbar_init(bar_a_free(i), NUM_CONVERTERS); }
+        for (int i = 0; i < p.sa; ++i) { mbar_init(bar_a_full(i), 1); mbar_init(bar_a_free(i), NUM_CONVERTER_WARPS); }
         for (int j = 0; j < p.sb; ++j) { mbar_init(bar_b_full(j), 1); mbar_init(bar_b_free(j), 1); }
-        for (int k = 0; k < p.st; ++k) { mbar_init(bar_t_ready(k), NUM_CONVERTERS); mbar_init(bar_t_free(k), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tmem_full(a), 1); mbar_init(bar_tmem_empty(a), 128); }
+        for (int k = 0; k < p.st; ++k) { mbar_init(bar_t_ready(k), NUM_CONVERTER_WARPS); mbar_init(bar_t_free(k), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tmem_full(a), 1); mbar_init(bar_tmem_empty(a), 4); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -397,7 +397,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
                 __syncwarp();
             }
             tc_fence_before();
-            mbar_arrive(bar_tmem_empty(a));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tmem_empty(a));
         }
     } else if (warp >= 8) {
         // =============================== converters ===============================
@@ -437,12 +438,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
                 if (p.passes == 3) tmem_st_x16(tmem_base + lane_addr + col + 32, lo);
                 tmem_st_wait();
                 tc_fence_before();
-                mbar_arrive(bar_t_ready(k));
-                // Release the smem slot only now: this arrive is ordered after the tcgen05.st of the values loaded
-                // from the slot.  Arriving right after the ld.shared (no register dependence on the loads) let the
-                // barrier unit overtake the load unit; the next TMA then overwrote rows that were still being read
-                // (seen as wrong pixel rows, but only on a CTA's 2nd+ tile, when the rings run full).
-                mbar_arrive(bar_a_free(i_prev));
+                // ONE arrival per warp on each barrier: with one per thread the 512 shared-memory barrier updates per
+                // slab (~2 cycles each) were the kernel's real limiter, ~1100 cycles per slab whatever else changed.
+                // The smem slot is released only here, after every lane's tcgen05.st of the values it loaded from the
+                // slot has completed.  Arriving right after the ld.shared (no register dependence on the loads) let
+                // the barrier unit overtake the load unit; the next TMA then overwrote rows that were still being
+                // read (seen as wrong pixel rows, but only on a CTA's 2nd+ tile, when the rings run full).
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bar_t_ready(k));
+                    mbar_arrive(bar_a_free(i_prev));
+                }
                 if (++k == p.st) { k = 0; phk ^= 1; }
             }
         }

@@ -80,9 +80,9 @@ def contraction(a: torch.Tensor, feats: torch.Tensor, *, precision: Optional[str
     flags = gemm_flags(precision, sigmoid)
     if pixel_major:
         Mp = (M + 3) & ~3
+        # the padding columns [M, Mp) are never exposed (`out` below) and every kernel that streams the buffer
+        # (decode_score, decode_threshold) ignores them, so they are left as the allocator returned them
         buf = torch.empty((B, h, w, Mp), device=feats.device, dtype=torch.float32)
-        if Mp != M:
-            buf[..., M:].zero_()
         s_cn, s_cp, s_c = 1, Mp, N * Mp
         out = buf[..., :M].permute(0, 3, 1, 2)
     else:

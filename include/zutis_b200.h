@@ -151,6 +151,28 @@ ZUTIS_API int zutis_unpack_mask_bits(const uint32_t* mask_bits, long n_masks, in
 ZUTIS_API int zutis_pairwise_mask_intersections(const uint32_t* mask_bits, int M, long words_per_mask,
                                                 int32_t* inter, void* stream);
 
+/* COCO run-length encoding + bounding boxes of bit-packed masks, on the device.
+ * Replaces pycocotools.mask.encode(np.asfortranarray(m)) (networks/zutis.py:290; cocoapi rleEncode: the mask flattened
+ * column by column, alternating run lengths starting with a possibly empty run of zeros) and
+ * torchvision.ops.masks_to_boxes (networks/zutis.py:294) for the masks that survive NMS.
+ * mask_bits: row-packed masks, mask i at mask_bits + id(i) * mask_stride_words, id(i) = mask_ids ? mask_ids[i] : i,
+ * each [H][(W+31)/32] words, bit x%32 of word [y][x/32] = pixel (y, x).
+ * Count pass (runs == NULL): n_runs[i] = number of runs, boxes[4i..] = {xmin, ymin, xmax, ymax} (inclusive pixel
+ * indices, -1 x4 for an empty mask; boxes may be NULL).  Write pass (runs != NULL): the n_runs[i] run lengths of mask
+ * i go to runs + run_offsets[i]; the caller derives run_offsets from the count pass.  H*W < 2^31; masks whose
+ * column-packed copy exceeds 200 KB of shared memory (about 1400 x 1024) return ZUTIS_ERR_UNSUPPORTED. */
+ZUTIS_API int zutis_mask_rle(const uint32_t* mask_bits, long mask_stride_words, const int32_t* mask_ids, int n_masks,
+                             int H, int W, const int64_t* run_offsets, uint32_t* runs, int32_t* n_runs, int32_t* boxes,
+                             void* stream);
+
+/* cocoapi rleToString on the device: the `counts` bytes of pycocotools.mask.encode (networks/zutis.py:290) from the run
+ * lengths zutis_mask_rle wrote.  Mask i's string has string_lengths[i] bytes at strings + string_offsets[i]; the
+ * strings are packed back to back in completion order behind *cursor (device counter, zeroed by the caller; its final
+ * value is the number of bytes needed -- nothing is written past `capacity`, 7 bytes per run always suffice). */
+ZUTIS_API int zutis_rle_to_string(const uint32_t* runs, const int64_t* run_offsets, const int32_t* n_runs, int n_masks,
+                                  uint8_t* strings, int64_t capacity, uint64_t* cursor, int64_t* string_offsets,
+                                  int32_t* string_lengths, void* stream);
+
 /* Low-resolution instance statistics                              networks/zutis.py:390-406
  * probs [B,Q,h,w] (strides as above), tokens [B,hw,D] channel-last contiguous.
  * sizes[b,q] = #(p > thr); psum[b,q] = sum of in-mask p; mean_tokens[b,q,:] = sum of in-mask tokens / (size+1e-7). */

@@ -295,3 +295,86 @@ def hard_nms(masks: np.ndarray, scores: np.ndarray, cats: np.ndarray,
                 continue
             kept.append((int(cat), int(i), float(s)))
     return kept
+
+
+# ----------------------------------------------------------------------------------------------- COCO RLE + boxes
+# The reference formats every kept instance mask with pycocotools.mask.encode(np.asfortranarray(m))
+# (networks/zutis.py:290) and torchvision.ops.masks_to_boxes (:294).  pycocotools is a third-party dependency
+# that is NOT vendored under /root/reference and is not installed here; the reference does not pin its version
+# (README.md:83: "conda install -c conda-forge pycocotools").  What follows restates the published algorithm of
+# cocoapi common/maskApi.c (rleEncode, rleToString, rleFrString), which has not changed since pycocotools 2.0.
+# Parity of the compressed string is therefore UNPINNED against the real library; the run lengths are pinned
+# against a direct numpy walk of the Fortran-order mask, the string against hand-derived vectors and a
+# decode round trip (tests/test_oracle_golden.py).
+
+def rle_counts(mask: np.ndarray) -> List[int]:
+    """cocoapi rleEncode: run lengths of the mask flattened column by column, starting with a run of zeros
+    (which is 0 long when the first pixel is set)."""
+    flat = np.asarray(mask).astype(bool).ravel(order="F")
+    counts: List[int] = []
+    prev, run = False, 0
+    for v in flat.tolist():
+        if v != prev:
+            counts.append(run)
+            run, prev = 0, v
+        run += 1
+    counts.append(run)
+    return counts
+
+
+def rle_counts_numpy(mask: np.ndarray) -> np.ndarray:
+    """Same run lengths, vectorised (for full-size masks)."""
+    flat = np.asarray(mask).astype(np.uint8).ravel(order="F")
+    change = np.flatnonzero(np.diff(flat)) + 1
+    bounds = np.concatenate(([0], change, [flat.size]))
+    runs = np.diff(bounds)
+    if flat.size and flat[0] == 1:
+        runs = np.concatenate(([0], runs))
+    return runs.astype(np.int64)
+
+
+def rle_to_string(counts) -> bytes:
+    """cocoapi rleToString: each count (from the fourth on: its difference to the count two places back) is
+    written as little-endian groups of 5 bits, bit 5 = "more groups follow", offset by 48 into printable ASCII;
+    negative differences are sign-extended (a group with bit 4 set ends the number when the rest is -1)."""
+    out = bytearray()
+    counts = [int(c) for c in counts]
+    for i, x in enumerate(counts):
+        if i > 2:
+            x -= counts[i - 2]
+        more = True
+        while more:
+            c = x & 0x1F
+            x >>= 5                                  # arithmetic shift: Python ints behave like C's signed long here
+            more = (x != -1) if (c & 0x10) else (x != 0)
+            if more:
+                c |= 0x20
+            out.append(c + 48)
+    return bytes(out)
+
+
+def rle_from_string(s: bytes) -> List[int]:
+    """cocoapi rleFrString (the inverse), used for round-trip checks."""
+    counts: List[int] = []
+    p = 0
+    while p < len(s):
+        x, k, more = 0, 0, True
+        while more:
+            c = s[p] - 48
+            x |= (c & 0x1F) << (5 * k)
+            more = bool(c & 0x20)
+            p += 1
+            k += 1
+            if not more and (c & 0x10):
+                x |= -1 << (5 * k)
+        if len(counts) > 2:
+            x += counts[-2]
+        counts.append(x)
+    return counts
+
+
+def mask_to_box(mask: np.ndarray) -> List[float]:
+    """torchvision.ops.masks_to_boxes for one mask (networks/zutis.py:294): [xmin, ymin, xmax, ymax] of the set
+    pixels as floats, inclusive indices."""
+    ys, xs = np.nonzero(np.asarray(mask))
+    return [float(xs.min()), float(ys.min()), float(xs.max()), float(ys.max())]

@@ -374,13 +374,61 @@ def test_instance_predict_drop_in(zb, golden, fixture, prefix, tag):
         assert set(p) >= {"category_id", "segmentation", "score", "image_id", "image_size", "bbox"}
         assert tuple(p["image_size"]) == (H, W)
         mask = np.unpackbits(rb)[: H * W].reshape(H, W).astype(bool)
-        seg = p["segmentation"]
-        if isinstance(seg, dict) and isinstance(seg.get("counts"), list):            # uncompressed COCO RLE
-            flat = np.zeros(H * W, np.uint8); pos = 0; val = 0
-            for run in seg["counts"]:
-                flat[pos:pos + run] = val; pos += run; val ^= 1
-            assert np.array_equal(flat.reshape(W, H).T.astype(bool), mask)
+        seg = p["segmentation"]                                   # pycocotools.mask.encode's dict, built on the device
+        assert seg["size"] == [H, W] and isinstance(seg["counts"], bytes)
+        assert seg["counts"] == O.rle_to_string(O.rle_counts_numpy(mask))
+        flat = np.zeros(H * W, np.uint8); pos = 0; val = 0
+        for run in O.rle_from_string(seg["counts"]):
+            flat[pos:pos + run] = val; pos += run; val ^= 1
+        assert pos == H * W and np.array_equal(flat.reshape(W, H).T.astype(bool), mask)
         assert p["bbox"] == list(box)
+
+
+def _pack_rows(masks: np.ndarray) -> np.ndarray:
+    """bool [n,H,W] -> int32 [n,H,ceil(W/32)], bit x%32 of word [y][x/32] = pixel (y,x)."""
+    n, H, W = masks.shape
+    words = (W + 31) // 32
+    padded = np.zeros((n, H, words * 32), np.uint8)
+    padded[:, :, :W] = masks
+    return np.packbits(padded.reshape(n, H, words, 32), axis=-1, bitorder="little").view(np.uint32).reshape(n, H, words).view(np.int32)
+
+
+@pytest.mark.parametrize("H,W", [(1, 1), (1, 70), (33, 1), (5, 32), (31, 33), (64, 64), (50, 70), (480, 640), (97, 1000)])
+def test_mask_rle_and_boxes_match_oracle(zb, H, W):
+    rng = np.random.default_rng(H * 1000 + W)
+    n = 12
+    masks = np.zeros((n, H, W), bool)
+    masks[1] = True                                                                  # full: runs [0, H*W]
+    masks[2, 0, 0] = True                                                            # starts with a set pixel
+    masks[3, -1, -1] = True                                                          # ends with a set pixel
+    masks[4] = rng.random((H, W)) < 0.5                                              # noise: ~H*W/2 runs
+    masks[5, :, W // 2:] = True                                                      # right half: one transition
+    masks[6, H // 2:, :] = True                                                      # bottom half: a run per column
+    yy, xx = np.mgrid[0:H, 0:W]
+    for i in range(7, n):                                                            # blobs
+        cy, cx, r = rng.uniform(0, H), rng.uniform(0, W), rng.uniform(0.5, max(H, W) / 2 + 1)
+        masks[i] = (yy - cy) ** 2 + (xx - cx) ** 2 < r * r
+    bits = torch.from_numpy(_pack_rows(masks)).cuda()
+    order = [3, 0, 7, 1, 2, 4, 5, 6, 8, 9, 10, 11, 4]                                # selection, repeats allowed
+    for ids in (None, torch.tensor(order)):
+        sel = masks if ids is None else masks[order]
+        n_runs, runs, boxes = zb.ops.mask_rle(bits, W, mask_ids=ids)
+        offs = np.cumsum(n_runs) - n_runs
+        for i, m in enumerate(sel):
+            want = O.rle_counts_numpy(m)
+            got = runs[offs[i]: offs[i] + n_runs[i]].astype(np.int64)
+            assert np.array_equal(got, want), (H, W, i)
+            if m.any():
+                assert [float(v) for v in boxes[i]] == O.mask_to_box(m)
+            else:
+                assert boxes[i].tolist() == [-1, -1, -1, -1]
+        from zutis_b200.decode import _rle_strings
+        strings = _rle_strings(n_runs, runs)                                         # host (numpy) compressor
+        dev_strings, dev_boxes = zb.ops.mask_rle_strings(bits, W, mask_ids=ids)      # device compressor
+        assert np.array_equal(dev_boxes, boxes)
+        for i, m in enumerate(sel):
+            want = O.rle_to_string(O.rle_counts_numpy(m))
+            assert strings[i] == want and dev_strings[i] == want
 
 
 # ----------------------------------------------------------------------------- host-buffer entry

@@ -17,6 +17,7 @@ meter.update(gt, labels); meter.get_scores()
 probs = torch.sigmoid(3 * torch.randn(2, 100, 15, 20, device="cuda"))
 bits, areas = ops.decode_threshold(probs, (120, 160), 0.5)
 ops.pairwise_mask_intersections(bits[0]); ops.unpack_mask_bits(bits[0], 160)
+ops.mask_rle(bits, 160); ops.mask_rle_strings(bits, 160, mask_ids=torch.tensor([3, 0, 5]))
 s, p, m = ops.instance_lowres_stats(probs, torch.randn(2, 15, 20, 512, device="cuda"), 0.5)
 ops.instance_categories(m, text, 5.0)
 ops.upsample_bilinear(lo2, (50, 60))

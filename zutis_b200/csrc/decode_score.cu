@@ -363,36 +363,44 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const
         __syncwarp();
         if (u + 1 < n_units) { cur = decode_unit(u + 1); stage(cur, tiles + (buf ^ 1) * tile_floats); }
 
-        // pad the last group with -inf; non-finite taps show up as |bits| >= 0x7f800000
-        unsigned amax = 0;
-        if (lane < ngroups) {
-            const bool last = (lane == ngroups - 1) && (qc & 3);
-            for (int pix = 0; pix < 2 * p.XR; ++pix) {
-                float4* q4 = reinterpret_cast<float4*>(tile + pix * p.QS) + lane;
-                float4 v = *q4;
-                if (last) {
-                    const int keep = qc & 3;
-                    if (keep < 2) v.y = -INFINITY;
-                    if (keep < 3) v.z = -INFINITY;
-                    v.w = -INFINITY;
-                    *q4 = v;
-                    amax = max(amax, __float_as_uint(v.x) & 0x7fffffffu);
-                    if (keep > 1) amax = max(amax, __float_as_uint(v.y) & 0x7fffffffu);
-                    if (keep > 2) amax = max(amax, __float_as_uint(v.z) & 0x7fffffffu);
+        // Pad the last group with -inf and look for non-finite taps: x * 0 + acc stays (+-)0 for finite x and turns
+        // into NaN for NaN / +-inf, which costs one packed FMA-pipe instruction per two taps.
+        unsigned long long poison = 0ull;                                 // packed (0.f, 0.f)
+        {
+            const int step4 = p.QS >> 2, npix = 2 * p.XR;
+            if (lane < ngroups) {
+                float4* q4 = reinterpret_cast<float4*>(tile) + lane;
+                if (!((lane == ngroups - 1) && (qc & 3))) {
+#pragma unroll 4
+                    for (int pix = 0; pix < npix; ++pix) {
+                        const float4 v = q4[pix * step4];
+                        poison = fma2(pack2(v.x, v.y), 0ull, poison);
+                        poison = fma2(pack2(v.z, v.w), 0ull, poison);
+                    }
                 } else {
-                    amax = max(max(amax, __float_as_uint(v.x) & 0x7fffffffu), max(__float_as_uint(v.y) & 0x7fffffffu,
-                               max(__float_as_uint(v.z) & 0x7fffffffu, __float_as_uint(v.w) & 0x7fffffffu)));
+                    const int keep = qc & 3;
+                    for (int pix = 0; pix < npix; ++pix) {
+                        float4 v = q4[pix * step4];
+                        poison = fma2(pack2(v.x, keep > 1 ? v.y : 0.f), 0ull, poison);
+                        poison = fma2(pack2(keep > 2 ? v.z : 0.f, 0.f), 0ull, poison);
+                        if (keep < 2) v.y = -INFINITY;
+                        if (keep < 3) v.z = -INFINITY;
+                        v.w = -INFINITY;
+                        q4[pix * step4] = v;
+                    }
+                }
+            }
+            for (int g = lane + 32; g < ngroups; g += 32) {               // QC > 128 never happens, kept for safety
+                for (int pix = 0; pix < npix; ++pix) {
+                    const float4 v = reinterpret_cast<const float4*>(tile)[pix * step4 + g];
+                    poison = fma2(pack2(v.x, v.y), 0ull, poison);
+                    poison = fma2(pack2(v.z, v.w), 0ull, poison);
                 }
             }
         }
-        for (int g = lane + 32; g < ngroups; g += 32) {                 // QC > 128 never happens, kept for safety
-            for (int pix = 0; pix < 2 * p.XR; ++pix) {
-                const float4 v = reinterpret_cast<const float4*>(tile + pix * p.QS)[g];
-                amax = max(max(amax, __float_as_uint(v.x) & 0x7fffffffu), max(__float_as_uint(v.y) & 0x7fffffffu,
-                           max(__float_as_uint(v.z) & 0x7fffffffu, __float_as_uint(v.w) & 0x7fffffffu)));
-            }
-        }
-        const bool chunk_finite = __all_sync(0xffffffffu, amax < 0x7f800000u);
+        float poison_x, poison_y;
+        unpack2(poison, poison_x, poison_y);
+        const bool chunk_finite = __all_sync(0xffffffffu, poison_x == 0.f && poison_y == 0.f);   // NaN compares false
         __syncwarp();
 
         if (un.ch == 0) {

@@ -3,11 +3,14 @@
 //   threshold_kernel        interp(probabilities) > threshold -> bit-packed masks    networks/zutis.py:422-425, :390
 //   unpack_bits_kernel      bit-packed -> one byte per pixel for legacy consumers
 //   pair_inter_kernel       popcount(mask_i & mask_j): the counts behind compute_iou  utils/iou.py:31-33 (NMS, zutis.py:258-259)
+//   mask_rle_kernel         column-major (COCO) run lengths + bounding box of a mask  networks/zutis.py:290, :294
 //   lowres_stats_kernel     mask sizes, in-mask probability sums, masked mean tokens  networks/zutis.py:390-406
 //   (the tiled threshold kernel lives in decode_score.cu next to the decode kernel whose staging it shares)
 //   categories_kernel       sigmoid(T * cos(text, mean token)) -> argmax / max        networks/zutis.py:409-420
 // Compiled with -fmad=false; interpolation uses the same explicit fma pattern as decode_score.cu.
 #include "common.cuh"
+
+#include <limits.h>
 
 namespace zutis {
 
@@ -94,6 +97,205 @@ __global__ void __launch_bounds__(256) pair_inter_kernel(const uint32_t* bits, i
         inter[(long)i * M + j] = s;
         inter[(long)j * M + i] = s;
     }
+}
+
+// COCO run-length encoding and bounding box of bit-packed masks, on the device.
+// Replaces, per kept mask, pycocotools.mask.encode(np.asfortranarray(m)) (networks/zutis.py:290; the run lengths that
+// cocoapi's rleEncode produces: the mask flattened COLUMN by column, alternating runs starting with a zero run that
+// may be empty) and torchvision.ops.masks_to_boxes (:294).  The reference ships every boolean mask to the host
+// (307 KB each at 480x640) and walks it there.
+// One block per mask:
+//   1. 32x32 bit-block transposes by warp ballots turn the row-packed mask (bit x of word [y][x/32]) into
+//      column-packed words in shared memory (bit y of word [x][y/32]);
+//   2. thread = column: t = c ^ ((c << 1) | carry) marks the positions where the column-major bit stream changes
+//      value (the carry into a column is the last bit of the previous column, 0 before the first); popcounts give the
+//      transitions per column, first/last set bits the box;
+//   3. a block scan turns the counts into output offsets and carries the last transition position across columns;
+//   4. (write pass) the set bits of t are walked again and every transition position p_k emits run k = p_k - p_(k-1),
+//      p_(-1) = 0; the closing run is H*W - p_(K-1).  A mask with K transitions has K+1 runs.
+// The caller runs the kernel twice: runs == nullptr counts (n_runs, boxes), then with exact offsets it writes.
+constexpr int kRleThreads = 256;
+
+__global__ void __launch_bounds__(kRleThreads) mask_rle_kernel(const uint32_t* __restrict__ bits, long mask_stride,
+                                                               const int* __restrict__ mask_ids, int H, int W, int words,
+                                                               int hw, int hwp, const long* __restrict__ run_offsets,
+                                                               uint32_t* __restrict__ runs, int* __restrict__ n_runs,
+                                                               int* __restrict__ boxes) {
+    extern __shared__ uint32_t s_col[];                      // [words*32][hwp] column-packed bits, hwp odd
+    const int wpad = words * 32;
+    int* s_cnt = reinterpret_cast<int*>(s_col + (size_t)wpad * hwp);    // [wpad] transitions per column -> exclusive offsets
+    int* s_last = s_cnt + wpad;                              // [wpad] last transition position of the column -> of all earlier columns
+    __shared__ int s_box[4];
+    __shared__ int s_warp_sum[kRleThreads / 32], s_warp_max[kRleThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long mask = mask_ids ? mask_ids[blockIdx.x] : (long)blockIdx.x;
+    const uint32_t* m = bits + mask * mask_stride;
+    if (threadIdx.x == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = -1; s_box[3] = -1; }
+
+    // ---- 1. transpose
+    const uint32_t tail_x = (W & 31) ? ((1u << (W & 31)) - 1u) : 0xffffffffu;
+    for (int blk = warp; blk < hw * words; blk += kRleThreads / 32) {
+        const int yb = blk / words, xb = blk % words;
+        const int y = yb * 32 + lane;
+        uint32_t r = y < H ? __ldg(m + (long)y * words + xb) : 0u;
+        if (xb == words - 1) r &= tail_x;
+        uint32_t mine = 0;
+#pragma unroll
+        for (int x = 0; x < 32; ++x) {
+            const uint32_t v = __ballot_sync(0xffffffffu, (r >> x) & 1u);
+            if (lane == x) mine = v;
+        }
+        s_col[(size_t)(xb * 32 + lane) * hwp + yb] = mine;
+    }
+    __syncthreads();
+
+    // ---- 2. transitions per column, box
+    const uint32_t tail_y = (H & 31) ? ((1u << (H & 31)) - 1u) : 0xffffffffu;
+    int xmin = INT_MAX, ymin = INT_MAX, xmax = -1, ymax = -1;
+    for (int x = threadIdx.x; x < wpad; x += kRleThreads) {
+        int cnt = 0, last = -1;
+        if (x < W) {
+            uint32_t carry = x > 0 ? (s_col[(size_t)(x - 1) * hwp + ((H - 1) >> 5)] >> ((H - 1) & 31)) & 1u : 0u;
+            for (int j = 0; j < hw; ++j) {
+                const uint32_t c = s_col[(size_t)x * hwp + j];
+                uint32_t t = c ^ ((c << 1) | carry);
+                if (j == hw - 1) t &= tail_y;
+                carry = c >> 31;
+                cnt += __popc(t);
+                if (t) last = x * H + j * 32 + (31 - __clz(t));
+                if (c) {
+                    ymin = min(ymin, j * 32 + __ffs(c) - 1);
+                    ymax = max(ymax, j * 32 + 31 - __clz(c));
+                    xmin = min(xmin, x);
+                    xmax = max(xmax, x);
+                }
+            }
+        }
+        s_cnt[x] = cnt;
+        s_last[x] = last;
+    }
+    if (xmax >= 0) { atomicMin(&s_box[0], xmin); atomicMin(&s_box[1], ymin); atomicMax(&s_box[2], xmax); atomicMax(&s_box[3], ymax); }
+    __syncthreads();
+
+    // ---- 3. exclusive scan of the counts / running maximum of the last positions; thread = a contiguous segment of columns
+    const int seg = (wpad + kRleThreads - 1) / kRleThreads;
+    const int x0 = threadIdx.x * seg, x1 = min(x0 + seg, wpad);
+    int sum = 0, mx = -1;
+    for (int x = x0; x < x1; ++x) { sum += s_cnt[x]; mx = max(mx, s_last[x]); }
+    int inc = sum, incmax = mx;                               // inclusive scans across the warp
+    for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, inc, o), bmax = __shfl_up_sync(0xffffffffu, incmax, o);
+        if (lane >= o) { inc += a; incmax = max(incmax, bmax); }
+    }
+    if (lane == 31) { s_warp_sum[warp] = inc; s_warp_max[warp] = incmax; }
+    __syncthreads();
+    int base = 0, basemax = -1, total = 0;
+    for (int k = 0; k < kRleThreads / 32; ++k) {
+        if (k < warp) { base += s_warp_sum[k]; basemax = max(basemax, s_warp_max[k]); }
+        total += s_warp_sum[k];
+    }
+    int ex = base + inc - sum;                                // transitions before this thread's segment
+    int exmax = max(basemax, __shfl_up_sync(0xffffffffu, incmax, 1));
+    if (lane == 0) exmax = basemax;
+    for (int x = x0; x < x1; ++x) {
+        const int c = s_cnt[x], l = s_last[x];
+        s_cnt[x] = ex; s_last[x] = exmax;
+        ex += c; exmax = max(exmax, l);
+    }
+    __syncthreads();
+
+    if (threadIdx.x == 0) {
+        n_runs[blockIdx.x] = total + 1;
+        if (boxes) {
+            const bool any = s_box[2] >= 0;
+            boxes[4 * blockIdx.x + 0] = any ? s_box[0] : -1; boxes[4 * blockIdx.x + 1] = any ? s_box[1] : -1;
+            boxes[4 * blockIdx.x + 2] = s_box[2]; boxes[4 * blockIdx.x + 3] = s_box[3];
+        }
+    }
+    if (!runs) return;
+
+    // ---- 4. emit the runs
+    uint32_t* out = runs + run_offsets[blockIdx.x];
+    for (int x = threadIdx.x; x < W; x += kRleThreads) {
+        int k = s_cnt[x];
+        int prev = max(s_last[x], 0);
+        uint32_t carry = x > 0 ? (s_col[(size_t)(x - 1) * hwp + ((H - 1) >> 5)] >> ((H - 1) & 31)) & 1u : 0u;
+        for (int j = 0; j < hw; ++j) {
+            const uint32_t c = s_col[(size_t)x * hwp + j];
+            uint32_t t = c ^ ((c << 1) | carry);
+            if (j == hw - 1) t &= tail_y;
+            carry = c >> 31;
+            while (t) {
+                const int b = __ffs(t) - 1;
+                t &= t - 1;
+                const int pos = x * H + j * 32 + b;
+                out[k++] = (uint32_t)(pos - prev);
+                prev = pos;
+            }
+        }
+    }
+    // closing run: everything after the last transition (s_last of a virtual column W = running max over all columns)
+    if (threadIdx.x == kRleThreads - 1) {
+        // ex / exmax of the last thread cover every column after its loop above
+        out[total] = (uint32_t)(H * W - max(exmax, 0));
+    }
+}
+
+// cocoapi rleToString on the device (the `counts` bytes pycocotools.mask.encode returns, networks/zutis.py:290).
+// From the fourth run of a mask on, the value written is the difference to the run two places back; a value becomes
+// little-endian groups of 5 bits, bit 5 = "more groups follow", +48; a group with bit 4 set ends the number once the
+// remaining sign-extended value is -1.  One block per mask: thread = a contiguous chunk of runs; sweep 1 counts the
+// characters, a block scan places the chunks, the block reserves its span of the output with one atomic on a cursor
+// (so the strings are packed back to back in completion order), sweep 2 writes.
+__device__ __forceinline__ int rle_chars(long long x, uint8_t* out) {
+    int n = 0;
+    bool more;
+    do {
+        int c = (int)(x & 0x1f);
+        x >>= 5;
+        more = (c & 0x10) ? (x != -1) : (x != 0);
+        if (more) c |= 0x20;
+        if (out) out[n] = (uint8_t)(c + 48);
+        ++n;
+    } while (more);
+    return n;
+}
+
+__global__ void __launch_bounds__(kRleThreads) rle_string_kernel(const uint32_t* __restrict__ runs, const long* __restrict__ run_offsets,
+                                                                 const int* __restrict__ n_runs, uint8_t* __restrict__ strings,
+                                                                 long capacity, unsigned long long* cursor,
+                                                                 long* __restrict__ string_offsets, int* __restrict__ string_lengths) {
+    __shared__ int s_warp[kRleThreads / 32];
+    __shared__ long s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = n_runs[blockIdx.x];
+    const uint32_t* r = runs + run_offsets[blockIdx.x];
+    const int chunk = (n + kRleThreads - 1) / kRleThreads;
+    const int i0 = min(threadIdx.x * chunk, n), i1 = min(i0 + chunk, n);
+    int len = 0;
+    for (int i = i0; i < i1; ++i) len += rle_chars((long long)r[i] - (i > 2 ? (long long)r[i - 2] : 0ll), nullptr);
+    int inc = len;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += a;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int k = 0; k < kRleThreads / 32; ++k) {
+        if (k < warp) before += s_warp[k];
+        total += s_warp[k];
+    }
+    if (threadIdx.x == 0) {
+        const long base = (long)atomicAdd(cursor, (unsigned long long)total);
+        s_base = base;
+        string_offsets[blockIdx.x] = base;
+        string_lengths[blockIdx.x] = total;
+    }
+    __syncthreads();
+    if (s_base + total > capacity) return;                   // reported through the cursor; the caller sized the buffer
+    uint8_t* out = strings + s_base + before + inc - len;
+    for (int i = i0; i < i1; ++i) out += rle_chars((long long)r[i] - (i > 2 ? (long long)r[i - 2] : 0ll), out);
 }
 
 // Low-resolution instance statistics (networks/zutis.py:390-406).  One block per (image, tile of kStatQ queries,
@@ -311,6 +513,42 @@ extern "C" int zutis_pairwise_mask_intersections(const uint32_t* mask_bits, int 
     if (st != ZUTIS_OK) return st;
     pair_inter_kernel<<<dim3(M, M), 256, 0, (cudaStream_t)stream>>>(mask_bits, M, words_per_mask, inter);
     return check_launch("pair_inter_kernel");
+}
+
+extern "C" int zutis_mask_rle(const uint32_t* mask_bits, long mask_stride_words, const int32_t* mask_ids, int n_masks,
+                              int H, int W, const int64_t* run_offsets, uint32_t* runs, int32_t* n_runs, int32_t* boxes,
+                              void* stream) {
+    ZUTIS_REQUIRE(mask_bits && n_runs, "zutis_mask_rle: NULL pointer");
+    ZUTIS_REQUIRE(n_masks >= 0 && H > 0 && W > 0, "zutis_mask_rle: bad shape");
+    ZUTIS_REQUIRE((long)H * W < 2147483647L, "zutis_mask_rle: H*W=%ld does not fit 31 bits", (long)H * W);
+    ZUTIS_REQUIRE(!runs || run_offsets, "zutis_mask_rle: the write pass needs run_offsets");
+    static_assert(sizeof(long) == sizeof(int64_t), "LP64 expected");
+    int st = current_device_ok();
+    if (st != ZUTIS_OK) return st;
+    if (n_masks == 0) return ZUTIS_OK;
+    const int words = (W + 31) / 32, hw = (H + 31) / 32, hwp = hw | 1;
+    const size_t smem = ((size_t)words * 32 * hwp + 2 * (size_t)words * 32) * 4;
+    if (smem > 200 * 1024)
+        return fail(ZUTIS_ERR_UNSUPPORTED, "zutis_mask_rle: a %dx%d mask needs %zu bytes of shared memory (limit 200 KB)", H, W, smem);
+    if (smem > 48 * 1024)
+        ZUTIS_CUDA(cudaFuncSetAttribute(mask_rle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mask_rle_kernel<<<(unsigned)n_masks, kRleThreads, smem, (cudaStream_t)stream>>>(
+        mask_bits, mask_stride_words, mask_ids, H, W, words, hw, hwp, reinterpret_cast<const long*>(run_offsets), runs, n_runs, boxes);
+    return check_launch("mask_rle_kernel");
+}
+
+extern "C" int zutis_rle_to_string(const uint32_t* runs, const int64_t* run_offsets, const int32_t* n_runs, int n_masks,
+                                   uint8_t* strings, int64_t capacity, uint64_t* cursor, int64_t* string_offsets,
+                                   int32_t* string_lengths, void* stream) {
+    ZUTIS_REQUIRE(runs && run_offsets && n_runs && strings && cursor && string_offsets && string_lengths, "zutis_rle_to_string: NULL pointer");
+    ZUTIS_REQUIRE(n_masks >= 0 && capacity >= 0, "zutis_rle_to_string: bad shape");
+    int st = current_device_ok();
+    if (st != ZUTIS_OK) return st;
+    if (n_masks == 0) return ZUTIS_OK;
+    rle_string_kernel<<<(unsigned)n_masks, kRleThreads, 0, (cudaStream_t)stream>>>(
+        runs, reinterpret_cast<const long*>(run_offsets), n_runs, strings, (long)capacity,
+        reinterpret_cast<unsigned long long*>(cursor), reinterpret_cast<long*>(string_offsets), string_lengths);
+    return check_launch("rle_string_kernel");
 }
 
 extern "C" int zutis_instance_lowres_stats(const float* probs, long sb, long sq, long sy, long sx,

@@ -32,36 +32,51 @@ from . import ops
 from .running_score import RunningScore
 
 
-def _encode_rle(mask_fortran: np.ndarray):
-    """``pycocotools.mask.encode`` when available (as the reference uses, zutis.py:290), else the
-    equivalent uncompressed COCO RLE (column-major run lengths starting with the zero run)."""
-    try:
-        from pycocotools.mask import encode  # type: ignore
-        return encode(mask_fortran)
-    except ImportError:
-        flat = np.asarray(mask_fortran, dtype=np.uint8).ravel(order="F")
-        change = np.flatnonzero(np.diff(flat)) + 1
-        bounds = np.concatenate(([0], change, [flat.size]))
-        runs = np.diff(bounds).tolist()
-        if flat.size and flat[0] == 1:
-            runs = [0] + runs
-        return {"size": [int(mask_fortran.shape[0]), int(mask_fortran.shape[1])], "counts": runs}
+def _rle_strings(n_runs: np.ndarray, runs: np.ndarray) -> List[bytes]:
+    """COCO compressed RLE strings for a batch of masks from their run lengths (``ops.mask_rle``).
+
+    This is cocoapi's ``rleToString`` (what ``pycocotools.mask.encode`` returns as ``counts``, zutis.py:290),
+    vectorised over every run of every mask at once: from the fourth run of a mask on, the value written is the
+    difference to the run two places back; each value becomes little-endian groups of 5 bits with bit 5 = "more
+    groups follow", +48; a group with bit 4 set ends a number once the remaining (sign-extended) value is -1."""
+    n_runs = np.asarray(n_runs, dtype=np.int64)
+    total = int(n_runs.sum())
+    if total == 0:
+        return [b"" for _ in n_runs]
+    offsets = np.cumsum(n_runs) - n_runs
+    x = runs.astype(np.int64)
+    idx = np.arange(total, dtype=np.int64) - np.repeat(offsets, n_runs)      # index of the run inside its mask
+    late = idx > 2
+    x[late] -= runs.astype(np.int64)[np.flatnonzero(late) - 2]
+    chars = np.zeros((total, 7), dtype=np.uint8)                             # |x| < 2^31 needs at most 7 groups
+    alive = np.ones(total, dtype=bool)
+    length = np.zeros(total, dtype=np.int64)
+    for k in range(7):
+        c = x & 0x1F
+        x >>= 5
+        more = np.where((c & 0x10) != 0, x != -1, x != 0)
+        c = np.where(more, c | 0x20, c) + 48
+        chars[:, k] = np.where(alive, c, 0)
+        length += alive
+        alive &= more
+        if not alive.any():
+            break
+    flat = chars[np.arange(7)[None, :] < length[:, None]]                    # row-major: run order, then group order
+    ends = np.cumsum(np.add.reduceat(length, offsets))
+    starts = ends - np.add.reduceat(length, offsets)
+    buf = flat.tobytes()
+    return [buf[a:b] for a, b in zip(starts.tolist(), ends.tolist())]
 
 
-def _mask_to_box(mask: np.ndarray) -> List[float]:
-    """torchvision.ops.masks_to_boxes for one mask: [xmin, ymin, xmax, ymax] as floats (zutis.py:294)."""
-    ys, xs = np.nonzero(mask)
-    return [float(xs.min()), float(ys.min()), float(xs.max()), float(ys.max())]
-
-
-def _prediction(mask: np.ndarray, score: float, label_id: int, image_id, label_id_to_category) -> dict:
+def _prediction(rle_counts: bytes, box: np.ndarray, size: Tuple[int, int], score: float, label_id: int, image_id,
+                label_id_to_category) -> dict:
     out = {
         "category_id": label_id,
-        "segmentation": _encode_rle(np.asfortranarray(mask)),
+        "segmentation": {"size": [int(size[0]), int(size[1])], "counts": rle_counts},   # pycocotools.mask.encode's dict
         "score": score,
         "image_id": image_id,
-        "image_size": mask.shape[-2:],
-        "bbox": _mask_to_box(mask),
+        "image_size": (int(size[0]), int(size[1])),
+        "bbox": [float(v) for v in box],                                                 # masks_to_boxes(...).tolist()
     }
     if label_id_to_category is not None:
         out["pred_class"] = label_id_to_category[label_id]
@@ -77,7 +92,8 @@ def _nms_keep(cats: np.ndarray, scores: np.ndarray, inter: np.ndarray, nms_type:
     Returns (category, query index, score) in the reference's emission order.
     """
     assert nms_type in ["hard", "linear", "gaussian"]
-    area = np.diag(inter).astype(np.int64)
+    inter = np.asarray(inter).tolist()                       # Python ints: exact, and much cheaper than numpy scalars below
+    area = [row[i] for i, row in enumerate(inter)]
     kept = []
     for cat in set(cats):
         if cat == 0:                      # background category
@@ -93,14 +109,14 @@ def _nms_keep(cats: np.ndarray, scores: np.ndarray, inter: np.ndarray, nms_type:
             chosen.append((top, top_score))
             survivors, survivor_scores = [], []
             for i, s in zip(cand[:-1], cand_scores[:-1]):
-                both = np.int64(inter[i, top])
-                iou = both / ((area[i] + area[top] - both) + 1e-7)
+                both = inter[i][top]
+                iou = both / ((area[i] + area[top] - both) + 1e-7)            # float64, as utils/iou.py:31-33
                 if nms_type == "hard":
                     weight = 0 if iou > nms_threshold else 1
                 elif nms_type == "linear":
-                    weight = (1 - iou) if iou > nms_threshold else 1
+                    weight = (1 - np.float64(iou)) if iou > nms_threshold else 1
                 else:
-                    weight = np.exp(-(iou * iou) / sigma)
+                    weight = np.exp(-(np.float64(iou) * iou) / sigma)
                 s = s * weight
                 if s > floor:
                     survivors.append(i); survivor_scores.append(s)
@@ -161,22 +177,27 @@ def predict(
 
     if image_ids is None:
         image_ids = [0 for _ in range(B)]
-    predictions: List[dict] = list()
-    for b, image_id in zip(range(B), image_ids):
+    # pairwise intersection counts of every image are enqueued first and fetched with one copy
+    inter_dev = torch.stack([ops.pairwise_mask_intersections(bits[b]) for b in range(B)])
+    inter_all = inter_dev.cpu().numpy()
+    kept: List[Tuple[int, int, int, float]] = []                   # (image, query, category, score), reference order
+    for b in range(min(B, len(image_ids))):                         # the reference zips range(B) with image_ids
         cats_b, conf_b = category_ids[b], confidence[b]
         if nms_type is None:
-            areas = ops.pairwise_mask_intersections(bits[b]).diagonal().cpu().numpy()
+            areas = inter_all[b].diagonal()
             keep = [(c, q, s) for q, (s, c) in enumerate(zip(conf_b, cats_b)) if areas[q] != 0 and c != 0]
         else:
-            inter = ops.pairwise_mask_intersections(bits[b]).cpu().numpy()
-            keep = _nms_keep(cats_b, conf_b, inter, nms_type)
-        if not keep:
-            continue
-        chosen = torch.as_tensor([q for _, q, _ in keep], device=bits.device)
-        masks = ops.unpack_mask_bits(bits[b].index_select(0, chosen), W).cpu().numpy()
-        for (c, q, s), m in zip(keep, masks):
-            label_id = new_label_id_to_old_label_id[c.item()] if new_label_id_to_old_label_id is not None else c.item()
-            predictions.append(_prediction(m, s.item(), label_id, image_id, label_id_to_category))
+            keep = _nms_keep(cats_b, conf_b, inter_all[b], nms_type)
+        kept.extend((b, q, c, s) for c, q, s in keep)
+    predictions: List[dict] = list()
+    if not kept:
+        return predictions
+    # run lengths + boxes of the kept masks straight from the bit-packed device masks (no boolean mask leaves the GPU)
+    ids = torch.as_tensor([b * Q + q for b, q, _, _ in kept], dtype=torch.int32)
+    strings, boxes = ops.mask_rle_strings(bits, W, mask_ids=ids)
+    for (b, q, c, s), counts, box in zip(kept, strings, boxes):
+        label_id = new_label_id_to_old_label_id[c.item()] if new_label_id_to_old_label_id is not None else c.item()
+        predictions.append(_prediction(counts, box, (H, W), s.item(), label_id, image_ids[b], label_id_to_category))
     return predictions
 
 

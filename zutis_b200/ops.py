@@ -8,6 +8,7 @@ from __future__ import annotations
 
 from typing import Optional, Tuple
 
+import numpy as np
 import torch
 
 from . import _ffi as F
@@ -222,6 +223,77 @@ def pairwise_mask_intersections(bits: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(bits.device):
         F.call("zutis_pairwise_mask_intersections", bits.contiguous().data_ptr(), M, words, inter.data_ptr(), _stream())
     return inter
+
+
+def _mask_rle_device(bits: torch.Tensor, W: int, mask_ids: Optional[torch.Tensor]):
+    """Both passes of zutis_mask_rle; everything but the run counts stays on the device."""
+    _need_cuda(bits, "bits")
+    H, words = bits.shape[-2], bits.shape[-1]
+    if words != (W + 31) // 32:
+        raise ValueError(f"bits has {words} words per row, W={W} needs {(W + 31) // 32}")
+    bits = bits.contiguous()
+    n_all = bits.numel() // (H * words)
+    ids = None
+    n = n_all
+    if mask_ids is not None:
+        ids_host = torch.as_tensor(mask_ids, dtype=torch.int64).cpu()
+        n = ids_host.numel()
+        if n and (int(ids_host.min()) < 0 or int(ids_host.max()) >= n_all):
+            raise ValueError("mask_ids out of range")
+        ids = ids_host.to(device=bits.device, dtype=torch.int32)
+    if n == 0:
+        return None
+    n_runs = torch.empty(n, device=bits.device, dtype=torch.int32)
+    boxes = torch.empty((n, 4), device=bits.device, dtype=torch.int32)
+    with torch.cuda.device(bits.device):
+        F.call("zutis_mask_rle", bits.data_ptr(), H * words, ids.data_ptr() if ids is not None else None, n, H, W,
+               None, None, n_runs.data_ptr(), boxes.data_ptr(), _stream())
+        counts = n_runs.cpu().numpy().astype(np.int64)
+        offsets = np.cumsum(counts) - counts
+        off_dev = torch.from_numpy(offsets).to(bits.device)
+        runs = torch.empty(int(counts.sum()), device=bits.device, dtype=torch.int32)
+        F.call("zutis_mask_rle", bits.data_ptr(), H * words, ids.data_ptr() if ids is not None else None, n, H, W,
+               off_dev.data_ptr(), runs.data_ptr(), n_runs.data_ptr(), None, _stream())
+    return counts, n_runs, off_dev, runs, boxes
+
+
+def mask_rle(bits: torch.Tensor, W: int, mask_ids: Optional[torch.Tensor] = None):
+    """COCO run lengths and boxes of bit-packed masks, computed on the device   (zutis.py:290, :294).
+
+    bits: int32 [..., H, words]; ``mask_ids`` (optional) selects and orders masks of the flattened leading dims.
+    Returns host arrays ``(n_runs int64 [n], runs uint32 [sum n_runs], boxes int32 [n,4])``: mask i owns
+    ``runs[offsets[i] : offsets[i] + n_runs[i]]`` with ``offsets = cumsum(n_runs) - n_runs`` -- the column-major run
+    lengths ``pycocotools.mask.encode`` compresses -- and ``boxes[i] = (xmin, ymin, xmax, ymax)`` (``-1`` if empty)."""
+    r = _mask_rle_device(bits, W, mask_ids)
+    if r is None:
+        return np.zeros(0, np.int64), np.zeros(0, np.uint32), np.zeros((0, 4), np.int32)
+    counts, _, _, runs, boxes = r
+    return counts, runs.cpu().numpy().view(np.uint32), boxes.cpu().numpy()
+
+
+def mask_rle_strings(bits: torch.Tensor, W: int, mask_ids: Optional[torch.Tensor] = None):
+    """``pycocotools.mask.encode(np.asfortranarray(m))["counts"]`` and ``masks_to_boxes`` for bit-packed device masks
+    (zutis.py:290, :294): run lengths, their compressed strings and the boxes are all produced on the device; the host
+    receives the run counts, then the packed strings -- no boolean mask is copied.  Returns ``(List[bytes], int32 [n,4])``."""
+    r = _mask_rle_device(bits, W, mask_ids)
+    if r is None:
+        return [], np.zeros((0, 4), np.int32)
+    counts, n_runs, off_dev, runs, boxes = r
+    n = counts.size
+    capacity = 7 * int(counts.sum())
+    strings = torch.empty(capacity, device=bits.device, dtype=torch.uint8)
+    meta = torch.zeros(1 + n, device=bits.device, dtype=torch.int64)          # [cursor | string offsets]
+    lengths = torch.empty(n, device=bits.device, dtype=torch.int32)
+    with torch.cuda.device(bits.device):
+        F.call("zutis_rle_to_string", runs.data_ptr(), off_dev.data_ptr(), n_runs.data_ptr(), n, strings.data_ptr(), capacity,
+               meta.data_ptr(), meta.data_ptr() + 8, lengths.data_ptr(), _stream())
+    meta_h = meta.cpu().numpy()
+    used = int(meta_h[0])
+    if used > capacity:
+        raise F.ZutisError(f"zutis_rle_to_string needed {used} bytes, {capacity} were provided")
+    buf = strings[:used].cpu().numpy().tobytes()
+    lens = lengths.cpu().numpy()
+    return [buf[o:o + l] for o, l in zip(meta_h[1:].tolist(), lens.tolist())], boxes.cpu().numpy()
 
 
 def instance_lowres_stats(probs: torch.Tensor, tokens: Optional[torch.Tensor], threshold: float = 0.5):

@@ -51,7 +51,10 @@ typedef enum {
     ZUTIS_DECODE_AUTO = 0,     /* fastest exact kernel the shape allows */
     ZUTIS_DECODE_GENERIC = 1,  /* one thread per output pixel, any scale/stride, NaN-exact */
     ZUTIS_DECODE_TILED = 2,    /* warp-tile kernel: low-res taps staged in shared memory */
-    ZUTIS_DECODE_PRUNED = 3    /* warp-per-cell kernel with exact candidate pruning */
+    ZUTIS_DECODE_PRUNED = 3,   /* warp-per-cell kernel with exact candidate pruning (needs a workspace) */
+    /* or-ed into the mode of zutis_decode_score_ws: the workspace already holds the champions of these logits
+     * (zutis_gemm_logits_champions reported champions_written = 1) */
+    ZUTIS_DECODE_CHAMPIONS_READY = 0x100
 } zutis_decode_mode;
 
 /* GEMM flags (bitwise or) */
@@ -94,6 +97,20 @@ ZUTIS_API int zutis_gemm_logits(const float* A, long lda, long strideA,
                                 int M, long N, int K, int batch, int flags,
                                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same contraction, which additionally leaves in `decode_workspace` (>= zutis_decode_workspace_bytes) what the
+ * candidate-pruning decode kernel needs per low-res pixel (first-max category, max |logit|) and per image (champion
+ * agreement of adjacent pixels, non-finite flag), computed in the epilogue while the logits are still in registers.
+ * img_w = low-res image width (N % img_w == 0).  *champions_written (host int, may be NULL) is set to 1 when the
+ * by-product was produced (tensor-core path, <= 256 categories, no sigmoid); pass ZUTIS_DECODE_CHAMPIONS_READY in the
+ * decode mode only in that case -- otherwise zutis_decode_score_ws computes the same data itself. */
+ZUTIS_API int zutis_gemm_logits_champions(const float* A, long lda, long strideA,
+                                          const float* Bm, long ldb, long strideB,
+                                          float* C, long stride_cn, long stride_cp, long strideC,
+                                          int M, long N, int K, int batch, int flags,
+                                          void* workspace, size_t workspace_bytes,
+                                          int img_w, void* decode_workspace, size_t decode_workspace_bytes,
+                                          int* champions_written, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (2)+(3)+(4) Fused bilinear upsample -> per-pixel argmax -> int16 labels -> confusion histogram.
  * Replaces F.interpolate(size, "bilinear") + torch.argmax(dim=1)   networks/zutis.py:366-372, trainer.py:169-173
@@ -114,6 +131,20 @@ ZUTIS_API int zutis_decode_score(const float* logits, long sb, long sq, long sy,
                                  const void* gt, int gt_dtype, long gt_sb,
                                  int16_t* labels, int32_t* hist_partial, int n_classes,
                                  int mode, void* stream);
+
+/* Same contract with a caller-provided device workspace (>= zutis_decode_workspace_bytes, 8-byte aligned), which
+ * enables the exact candidate-pruning kernel: per low-res cell only the categories that no corner champion dominates
+ * at all four corner taps are interpolated (monotonicity of the bilinear expression, csrc/decode_score.cu).  Results
+ * are identical to zutis_decode_score; ZUTIS_DECODE_AUTO sends each finite, spatially coherent image through the
+ * pruned kernel and the others through the tiled kernel, ZUTIS_DECODE_PRUNED forces every finite image through it
+ * (needs category index contiguous, sq == 1, and >= 4x up-sampling).  workspace == NULL behaves like
+ * zutis_decode_score. */
+ZUTIS_API size_t zutis_decode_workspace_bytes(int B, int Q, int h, int w, int H, int W);
+ZUTIS_API int zutis_decode_score_ws(const float* logits, long sb, long sq, long sy, long sx,
+                                    int B, int Q, int h, int w, int H, int W,
+                                    const void* gt, int gt_dtype, long gt_sb,
+                                    int16_t* labels, int32_t* hist_partial, int n_classes,
+                                    int mode, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Histogram only, for labels that already exist (RunningScore.update with device tensors).
  * pred: int16/int32/int64/u8 labels (pred_dtype uses zutis_gt_dtype), same element count as gt. */

@@ -198,6 +198,103 @@ def test_nan_and_inf_follow_torch_argmax(zb):
     assert np.array_equal(zb.ops.decode_score(wide.cuda(), (80, 80), mode=_ffi.DECODE_TILED).cpu().numpy(), want)
 
 
+def _smooth_logits(B, Q, h, w, gen, contrast=1.0):
+    """spatially coherent logits: a coarse random field up-sampled x4 (what a segmentation model emits)"""
+    coarse = torch.randn(B, Q, (h + 3) // 4 + 1, (w + 3) // 4 + 1, generator=gen)
+    return (contrast * torch.nn.functional.interpolate(coarse, size=(h, w), mode="bilinear", align_corners=True)).contiguous()
+
+
+@pytest.mark.parametrize("case", ["smooth", "smooth_noninteger", "x16", "x6", "iid", "ties", "nonfinite_mix", "wide", "hist_only"])
+def test_pruned_kernel_is_exact(zb, case):
+    """The candidate-pruning kernel must give the generic kernel's labels and histogram bit for bit -- on coherent
+    logits (where it prunes), on noise (where nearly everything survives), on exact ties and duplicated categories
+    (first maximum wins), and next to images with NaN/inf (which it must leave to the NaN-aware tiled kernel)."""
+    from zutis_b200 import _ffi
+    gen = torch.Generator().manual_seed(hash(case) % 1000 if False else len(case) * 7 + 1)
+    want_labels = True
+    if case == "smooth":
+        B, Q, h, w, H, W = 3, 81, 20, 24, 160, 192; lo = _smooth_logits(B, Q, h, w, gen, 0.1)
+    elif case == "smooth_noninteger":
+        B, Q, h, w, H, W = 2, 81, 13, 17, 107, 139; lo = _smooth_logits(B, Q, h, w, gen)
+    elif case == "x16":
+        B, Q, h, w, H, W = 2, 81, 14, 14, 224, 224; lo = _smooth_logits(B, Q, h, w, gen)
+    elif case == "x6":
+        B, Q, h, w, H, W = 2, 21, 16, 20, 96, 120; lo = _smooth_logits(B, Q, h, w, gen)
+    elif case == "iid":
+        B, Q, h, w, H, W = 2, 81, 10, 12, 80, 96; lo = torch.randn(B, Q, h, w, generator=gen)
+    elif case == "ties":
+        B, Q, h, w, H, W = 3, 24, 9, 9, 72, 72
+        lo = _smooth_logits(B, Q, h, w, gen)
+        lo[:, 5] = lo[:, 17]; lo[:, 20] = lo[:, 2]                     # duplicated categories: the smaller index must win
+        lo[1] = 0.0                                                       # a constant image: label 0 everywhere
+        lo[2] = torch.round(lo[2] * 2) / 2                                # heavy exact ties between different categories
+    elif case == "nonfinite_mix":
+        B, Q, h, w, H, W = 4, 40, 8, 10, 64, 80
+        lo = _smooth_logits(B, Q, h, w, gen)
+        lo[1, 7, 3, 4] = float("nan"); lo[3, 2, 0, 0] = float("inf"); lo[3, 9, 7, 9] = float("-inf")
+    elif case == "wide":
+        B, Q, h, w, H, W = 1, 920, 7, 8, 56, 64; lo = _smooth_logits(B, Q, h, w, gen, 0.2)
+    else:
+        B, Q, h, w, H, W = 2, 81, 10, 10, 80, 80; lo = _smooth_logits(B, Q, h, w, gen); want_labels = False
+    gt = torch.randint(0, Q, (B, H, W), generator=gen); gt[:, :3] = 1000
+    t = pixel_major(lo.cuda())
+    ref_part = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
+    ref = zb.ops.decode_score(t, (H, W), gt=gt.cuda(), hist_partial=ref_part, mode=_ffi.DECODE_GENERIC)
+    if case != "wide":
+        assert np.array_equal(ref.cpu().numpy().astype(np.int64), O.c_decode_semantic(lo.numpy(), (H, W)))
+    for mode in (_ffi.DECODE_PRUNED, _ffi.DECODE_AUTO):
+        part = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
+        got = zb.ops.decode_score(t, (H, W), gt=gt.cuda(), hist_partial=part, mode=mode, want_labels=want_labels)
+        if want_labels:
+            assert torch.equal(got, ref), f"{case}: labels differ in mode {mode}: {(got != ref).sum().item()} pixels"
+        assert torch.equal(part, ref_part), f"{case}: histogram differs in mode {mode}"
+        if want_labels:                                                  # labels without a histogram
+            assert torch.equal(zb.ops.decode_score(t, (H, W), mode=mode), ref)
+    # the pruned kernel needs contiguous categories; a query-major tensor must be refused in forced mode, not mis-read
+    with pytest.raises(zb.ZutisUnsupported):
+        zb.ops.decode_score(lo.cuda(), (H, W), mode=_ffi.DECODE_PRUNED)
+    assert torch.equal(zb.ops.decode_score(lo.cuda(), (H, W)), ref)
+
+
+def test_contraction_epilogue_champions_equal_decode_prepass(zb):
+    """zutis_gemm_logits_champions must leave in the workspace what the decode kernel's own pre-pass computes
+    (same champions, non-finite flags, and an agreement count on the same side of the threshold), and
+    decode_and_score must use it and still match the generic kernel bit for bit."""
+    from zutis_b200 import _ffi
+    gen = torch.Generator().manual_seed(3)
+    B, Q, D, h, w, H, W = 5, 81, 512, 20, 24, 160, 192
+    text = torch.nn.functional.normalize(torch.randn(Q, D, generator=gen), dim=-1).cuda()
+    coarse = torch.randn(B, D, h // 2, w // 2, generator=gen)
+    tokens = torch.nn.functional.normalize(torch.nn.functional.interpolate(coarse, scale_factor=2, mode="bilinear").permute(0, 2, 3, 1), dim=-1).contiguous().cuda()
+    tokens[3] = torch.nn.functional.normalize(torch.randn(h, w, D, generator=gen), dim=-1).cuda()     # an incoherent image -> tiled kernel
+    tokens[4, 2, 3, 7] = float("nan")                                                                  # a non-finite image -> tiled kernel
+    gt = torch.randint(0, Q, (B, H, W), generator=gen).cuda()
+    ws = zb.ops.DecodeWorkspace()
+    lo = zb.ops.contraction(text, tokens, precision="tf32x3", decode_ws=ws)
+    assert ws.ready_for == (lo.data_ptr(), (B, Q, h, w))
+    n = B * h * w
+    champ_gemm = ws.buf[: n * 8].view(torch.int32).view(n, 2).clone()
+    stats_gemm = ws.buf[n * 8: n * 8 + 8 * B].view(torch.int32).clone()
+    part = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
+    got = zb.ops.decode_score(lo, (H, W), gt=gt, hist_partial=part, workspace=ws)                      # READY path
+    ws2 = zb.ops.DecodeWorkspace()
+    part2 = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
+    got2 = zb.ops.decode_score(lo, (H, W), gt=gt, hist_partial=part2, workspace=ws2)                   # own pre-pass
+    champ_own = ws2.buf[: n * 8].view(torch.int32).view(n, 2)
+    stats_own = ws2.buf[n * 8: n * 8 + 8 * B].view(torch.int32)
+    finite = (stats_own[B:] == 0).repeat_interleave(h * w)
+    assert torch.equal(champ_gemm[finite], champ_own[finite])
+    assert torch.equal(stats_gemm[B:] != 0, stats_own[B:] != 0) and stats_own[B:].tolist() == [0, 0, 0, 0, 1]
+    thr = (h * (w - 1) + 9) // 10
+    assert torch.equal(stats_gemm[:B] >= thr, stats_own[:B] >= thr) and (stats_own[:4] >= thr).tolist() == [True, True, True, False]
+    ref_part = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
+    ref = zb.ops.decode_score(lo, (H, W), gt=gt, hist_partial=ref_part, mode=_ffi.DECODE_GENERIC)
+    assert torch.equal(got, ref) and torch.equal(got2, ref) and torch.equal(part, ref_part) and torch.equal(part2, ref_part)
+    meter = zb.RunningScore(Q)
+    labels = zb.decode_and_score(text, tokens, gt, (H, W), meter, want_labels=True, precision="tf32x3")
+    assert torch.equal(labels, ref) and torch.equal(meter.counts().view(-1).to(torch.int32), ref_part)
+
+
 @pytest.mark.parametrize("gt_dtype", [torch.uint8, torch.int16, torch.int32, torch.int64])
 def test_fused_histogram_bit_exact(zb, gt_dtype):
     from zutis_b200 import _ffi

@@ -45,7 +45,18 @@ struct DecodeParams {
     int vec_stage;   // taps can be staged with 16-byte cp.async (category index contiguous and aligned)
     int gt_bytes;    // sizeof one ground-truth label
     long n_items;    // B * n_groups * XB
+    // image selection between the tiled and the pruned kernel (workspace path only)
+    int select;              // 0: every image; 1: images the pruned kernel does NOT take; 2: images it takes
+    int agree_min;           // an image is pruned when it is finite and >= agree_min neighbouring low-res pixels share their champion
+    const int* img_stats;    // [B] neighbour agreements | [B] non-finite flags, written by champion_kernel
+    const int2* champ;       // [B*h*w] (first-max category, bits of max |logit|) per low-res pixel
+    int cap;                 // candidate slots per warp in the pruned kernel
+    int off_warp;            // byte offset of the pruned kernel's per-warp areas in dynamic shared memory
 };
+
+__device__ __forceinline__ bool image_is_pruned(const DecodeParams& p, int b) {
+    return p.img_stats[p.B + b] == 0 && p.img_stats[b] >= p.agree_min;
+}
 
 // ------------------------------------------------------------------------------ generic kernel
 __global__ void __launch_bounds__(256) decode_generic_kernel(const DecodeParams p) {
@@ -248,6 +259,21 @@ __device__ __forceinline__ void finish_rows(const DecodeParams& p, const Unit& u
     }
 }
 
+// the images this kernel owns, in ascending order (select: 1 = not pruned, 2 = pruned); one warp, B <= 1024
+__device__ __forceinline__ void build_image_list(const DecodeParams& p, int want_pruned, int* s_img, int* s_nimg) {
+    if (threadIdx.x < 32) {
+        int n = 0;
+        for (int b0 = 0; b0 < p.B; b0 += 32) {
+            const int b = b0 + (int)threadIdx.x;
+            const bool mine = b < p.B && (image_is_pruned(p, b) == (want_pruned != 0));
+            const unsigned bal = __ballot_sync(0xffffffffu, mine);
+            if (mine) s_img[n + __popc(bal & ((1u << threadIdx.x) - 1u))] = b;
+            n += __popc(bal);
+        }
+        if (threadIdx.x == 0) *s_nimg = n;
+    }
+}
+
 __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const DecodeParams p) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31;
@@ -260,7 +286,16 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const
     float2* s_ly = reinterpret_cast<float2*>(s_groups + p.n_groups);             // [H]: (ly0, ly1)
     const int row_stride = p.XR * p.QS;                                          // floats between the two staged rows
     const int tile_floats = 2 * row_stride;
-    float* tiles = reinterpret_cast<float*>(s_ly + ((p.H + 1) & ~1)) + warp * (2 * tile_floats);
+    int* s_img = reinterpret_cast<int*>(s_ly + ((p.H + 1) & ~1));                // [B] images of this launch (select != 0)
+    float* tiles = reinterpret_cast<float*>(s_img + (p.select ? ((p.B + 3) & ~3) : 0)) + warp * (2 * tile_floats);
+    __shared__ int s_nimg;
+
+    // ---- which images are ours (the pruned kernel takes the finite, spatially coherent ones)
+    if (p.select) {
+        build_image_list(p, p.select == 2, s_img, &s_nimg);
+        __syncthreads();
+        if (s_nimg == 0) return;
+    }
 
     // ---- per-CTA tables
     for (int i = threadIdx.x; i < nn && p.hist_in_smem; i += blockDim.x) s_hist[i] = 0;
@@ -286,7 +321,7 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const
     // (32-bit index math: the host guarantees n_items * nchunk < 2^31 and per-image offsets < 2^31)
     const unsigned first_item = blockIdx.x * kTiledWarps + warp;
     const unsigned item_stride = gridDim.x * kTiledWarps;
-    const unsigned total_items = (unsigned)p.n_items;
+    const unsigned total_items = p.select ? (unsigned)s_nimg * (unsigned)p.n_groups * (unsigned)p.XB : (unsigned)p.n_items;
     const unsigned my_items = first_item < total_items ? (total_items - first_item + item_stride - 1) / item_stride : 0;
     const unsigned n_units = my_items * nchunk;
     const int sx = (int)p.sx, sy = (int)p.sy, sq = (int)p.sq;
@@ -300,6 +335,7 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const
         const unsigned t = item / (unsigned)p.XB;
         const int4 grp = s_groups[t % (unsigned)p.n_groups];
         un.b = (int)(t / (unsigned)p.n_groups);
+        if (p.select) un.b = s_img[un.b];
         un.cy = grp.x; un.Y0 = grp.y; un.nr = grp.z;
         un.rx_lo = axis_tap(un.xb * 32, p.w, p.W, p.scale_x).i0;
         return un;
@@ -493,6 +529,337 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const
             const int v = s_hist[i];
             if (v) atomicAdd(p.hist + i, v);
         }
+    }
+}
+
+
+// ------------------------------------------------------------------------------ pruned decode
+// Exact candidate pruning per low-res CELL (the output pixels that share their top-left tap (cy, cx)).
+//
+// Every interpolant is  v_q = fma(ly0, fma(lx0, A_q, lx1*B_q), ly1 * fma(lx0, C_q, lx1*D_q))  of the cell's four
+// corner logits with non-negative weights, and every rounding in that expression is monotone in the taps.  Hence if
+// A_k >= A_j, B_k >= B_j, C_k >= C_j and D_k >= D_j then v_k >= v_j at EVERY pixel of the cell, in floating point.
+// Category j can therefore never be the first maximum anywhere in the cell when some k dominates it that way and
+//   * k < j (a tie still goes to k), or
+//   * k > j and the dominance holds with a margin m = 2^-20 * max|logit at the four corners|: the exact difference is
+//     then >= m * (1 - 2^-22) while three roundings per interpolant move the two values by at most 6 * 2^-24 * max|.|
+//     together, so v_k > v_j strictly.
+// Only the four corner champions (first maxima of the corner pixels, found once per low-res pixel by champion_kernel)
+// are tried as dominators.  On model-like logits 6 of 81 categories survive per cell (22 of 920); the survivors'
+// corner values are compacted into shared memory and the warp (lane = pixel of an 8x8 tile, 2 pixels per lane) walks
+// only those, in ascending category order with a strict compare = torch.argmax's first maximum.
+// A warp walks a run of kCellRun horizontally adjacent cells: the right corners (B, D) of one cell are the left
+// corners (A, C) of the next and stay in registers (NQ = ceil(Q/32) values per lane and corner, NQ = 0: wide Q, taps
+// re-read per cell).  The ground truth of a cell's first tile is requested before the pruning work so that its
+// latency is hidden.
+// Images with a non-finite logit (NaN ordering) or without spatial coherence (pruning would not pay) are left to the
+// tiled kernel; both kernels derive the same image split from champion_kernel's per-image counters.
+constexpr int kPrunedWarps = 8;
+constexpr int kCellRun = 8;
+
+// Per low-res pixel: first-max category and max |logit|; per image: the number of horizontally adjacent pixels that
+// share their champion and a non-finite flag.  One block per (image, low-res row); 8 lanes per pixel read the pixel's
+// categories as float4 (category index contiguous, 16-byte aligned pixels), 4 pixels per warp at a time.
+__global__ void __launch_bounds__(256) champion_kernel(const float* __restrict__ logits, long sb, long sy, long sx, int B, int Q,
+                                                       int h, int w, int2* __restrict__ champ, int* __restrict__ stats) {
+    extern __shared__ int s_row[];                            // [w]
+    __shared__ int s_agree[8];
+    const int b = blockIdx.x / h, y = blockIdx.x % h;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane & 7, grp = lane >> 3;
+    const float* row = logits + (long)b * sb + (long)y * sy;
+    const int chunks = (Q + 3) >> 2;
+    bool bad = false;
+    for (int x0 = warp * 4; x0 < w; x0 += 32) {
+        const int x = x0 + grp;
+        float best = -INFINITY, amax = 0.f;
+        int idx = 0x7fffffff;
+        if (x < w) {
+            const float4* v = reinterpret_cast<const float4*>(row + (long)x * sx);
+            for (int c = sub; c < chunks; c += 8) {
+                const float4 f = __ldg(v + c);
+                const float e[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int q = c * 4 + j;
+                    if (q < Q) {
+                        const float af = fabsf(e[j]);
+                        bad = bad || !(af <= 3.402823466e38f);
+                        amax = fmaxf(amax, af);
+                        if (e[j] > best || idx == 0x7fffffff) { best = e[j]; idx = q; }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+            if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+        }
+        if (sub == 0 && x < w) {
+            champ[((long)b * h + y) * w + x] = make_int2(idx, __float_as_int(amax));
+            s_row[x] = idx;
+        }
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (bad && lane == 0) atomicOr(stats + B + b, 1);
+    __syncthreads();
+    int agree = 0;
+    for (int x = threadIdx.x; x + 1 < w; x += blockDim.x) agree += (s_row[x] == s_row[x + 1]);
+    for (int o = 16; o > 0; o >>= 1) agree += __shfl_xor_sync(0xffffffffu, agree, o);
+    if (lane == 0) s_agree[warp] = agree;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int k = 0; k < 8; ++k) t += s_agree[k];
+        if (t) atomicAdd(stats + b, t);
+    }
+}
+
+template <typename GT, int NQ>
+__global__ void __launch_bounds__(kPrunedWarps * 32, 3) decode_pruned_kernel(const DecodeParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nn = p.n * p.n;
+    int* s_hist = reinterpret_cast<int*>(smem);
+    const int hist_words = p.hist_in_smem ? ((nn + 3) & ~3) : 0;
+    int* s_ystart = s_hist + hist_words;                                          // [h+1]
+    int* s_xstart = s_ystart + ((p.h + 1 + 3) & ~3);                              // [w+1]
+    float2* s_ly = reinterpret_cast<float2*>(s_xstart + ((p.w + 1 + 3) & ~3));    // [H]
+    float2* s_lx = s_ly + ((p.H + 1) & ~1);                                       // [W]
+    int* s_img = reinterpret_cast<int*>(s_lx + ((p.W + 1) & ~1));                 // [B]
+    // per-warp areas behind the tables (offset computed by the host): survivors' corner values (A, C, B, D), their
+    // categories, the champions' corner values.
+    char* warp_area = reinterpret_cast<char*>(smem) + p.off_warp;
+    float4* s_val = reinterpret_cast<float4*>(warp_area) + warp * p.cap;
+    int* s_list = reinterpret_cast<int*>(warp_area + (size_t)kPrunedWarps * p.cap * 16) + warp * p.cap;
+    float* s_champ = reinterpret_cast<float*>(warp_area + (size_t)kPrunedWarps * p.cap * 20) + warp * 16;
+    __shared__ int s_nimg;
+
+    build_image_list(p, 1, s_img, &s_nimg);
+    __syncthreads();
+    if (s_nimg == 0) return;
+
+    for (int i = threadIdx.x; i < nn && p.hist_in_smem; i += blockDim.x) s_hist[i] = 0;
+    for (int c = threadIdx.x; c <= p.h; c += blockDim.x) s_ystart[c] = first_dst_with_tap_ge(c, p.h, p.H, p.scale_y);
+    for (int c = threadIdx.x; c <= p.w; c += blockDim.x) s_xstart[c] = first_dst_with_tap_ge(c, p.w, p.W, p.scale_x);
+    for (int Y = threadIdx.x; Y < p.H; Y += blockDim.x) { const AxisTap t = axis_tap(Y, p.h, p.H, p.scale_y); s_ly[Y] = make_float2(t.l0, t.l1); }
+    for (int X = threadIdx.x; X < p.W; X += blockDim.x) { const AxisTap t = axis_tap(X, p.w, p.W, p.scale_x); s_lx[X] = make_float2(t.l0, t.l1); }
+    __syncthreads();
+    int* hist = p.hist ? (p.hist_in_smem ? s_hist : p.hist) : nullptr;
+    const GT* gt_base = reinterpret_cast<const GT*>(p.gt);
+
+    const int sx = (int)p.sx, sy = (int)p.sy;
+    const unsigned runs_per_row = (unsigned)(p.w + kCellRun - 1) / kCellRun;
+    const unsigned runs_per_image = runs_per_row * (unsigned)p.h;
+    const unsigned total = (unsigned)s_nimg * runs_per_image;
+    for (unsigned item = blockIdx.x * kPrunedWarps + warp; item < total; item += gridDim.x * kPrunedWarps) {
+        const unsigned slot = item / runs_per_image;
+        const unsigned rr = item - slot * runs_per_image;
+        const int cy = (int)(rr / runs_per_row);
+        const int cx_begin = (int)(rr - (unsigned)cy * runs_per_row) * kCellRun;
+        const int cx_end = min(cx_begin + kCellRun, p.w);
+        const int b = s_img[slot];
+        const int ys = s_ystart[cy], ye = s_ystart[cy + 1];
+        if (ys >= ye) continue;
+        const int cy1 = min(cy + 1, p.h - 1);
+        const float* row0 = p.logits + (long)b * p.sb + cy * sy;      // taps of the cells' upper corners
+        const float* row1 = p.logits + (long)b * p.sb + cy1 * sy;     //                    lower corners
+        const int2* ch0 = p.champ + ((size_t)b * p.h + cy) * p.w;
+        const int2* ch1 = p.champ + ((size_t)b * p.h + cy1) * p.w;
+        // per-lane bases: lane = (row lane/8 [+4], column lane%8) of an 8x8 pixel tile; category lane (+32, +64, ..) of a tap
+        const size_t lane_px = (size_t)(ys + (lane >> 3)) * p.W + (lane & 7);
+        int16_t* lbl_lane = p.labels ? p.labels + (size_t)b * p.H * p.W + lane_px : nullptr;
+        const GT* gt_lane = gt_base + (size_t)b * p.gt_sb + lane_px;
+        const float* row0_lane = row0 + lane;
+        const float* row1_lane = row1 + lane;
+        const int W4 = 4 * p.W;
+
+        // left corners of the first cell
+        float la_[NQ > 0 ? NQ : 1], lc_[NQ > 0 ? NQ : 1];
+        if (NQ > 0) {
+#pragma unroll
+            for (int it = 0; it < NQ; ++it) {
+                const bool qv = it * 32 + lane < p.Q;
+                la_[it] = qv ? __ldg(row0_lane + cx_begin * sx + it * 32) : 0.f;
+                lc_[it] = qv ? __ldg(row1_lane + cx_begin * sx + it * 32) : 0.f;
+            }
+        }
+        int2 hA = __ldg(ch0 + cx_begin), hC = __ldg(ch1 + cx_begin);
+
+        for (int cx = cx_begin; cx < cx_end; ++cx) {
+            const int cx1 = min(cx + 1, p.w - 1);
+            const int xs = s_xstart[cx], xe = s_xstart[cx + 1];
+            const float* pA = row0 + cx * sx;
+            const float* pB = row0 + cx1 * sx;
+            const float* pC = row1 + cx * sx;
+            const float* pD = row1 + cx1 * sx;
+            const int2 hB = __ldg(ch0 + cx1), hD = __ldg(ch1 + cx1);
+            // right corners (they become the next cell's left corners)
+            float rb_[NQ > 0 ? NQ : 1], rd_[NQ > 0 ? NQ : 1];
+            if (NQ > 0) {
+#pragma unroll
+                for (int it = 0; it < NQ; ++it) {
+                    const bool qv = it * 32 + lane < p.Q;
+                    rb_[it] = qv ? __ldg(row0_lane + cx1 * sx + it * 32) : 0.f;
+                    rd_[it] = qv ? __ldg(row1_lane + cx1 * sx + it * 32) : 0.f;
+                }
+            }
+            // ground truth of the first tile, requested now, used after the evaluation
+            const int Xf = xs + (lane & 7), Yf0 = ys + (lane >> 3), Yf1 = Yf0 + 4;
+            const bool okxf = Xf < xe, okf0 = okxf && Yf0 < ye, okf1 = okxf && Yf1 < ye;
+            GT g0 = (GT)0, g1 = (GT)0;
+            if (hist) {
+                if (okf0) g0 = gt_lane[xs];
+                if (okf1) g1 = gt_lane[xs + W4];
+            }
+            if (xs < xe) {
+                const int kk[4] = {hA.x, hB.x, hC.x, hD.x};
+                // 2^-20 * max|corner logits|, never 0: a champion must not dominate itself (its differences are exactly 0)
+                const float margin = fmaxf(fmaxf(fmaxf(__int_as_float(hA.y), __int_as_float(hB.y)), fmaxf(__int_as_float(hC.y), __int_as_float(hD.y))) * 9.5367431640625e-07f, 1e-37f);
+                const bool use[4] = {true, kk[1] != kk[0], kk[2] != kk[0] && kk[2] != kk[1], kk[3] != kk[0] && kk[3] != kk[1] && kk[3] != kk[2]};
+
+                // the champions' values at the four corners: lane 4c+r fetches corner r of champion c
+                __syncwarp();
+                if (lane < 16) {
+                    const int c = lane >> 2, r = lane & 3;
+                    const int k = c == 0 ? kk[0] : c == 1 ? kk[1] : c == 2 ? kk[2] : kk[3];
+                    const float* pr = r == 0 ? pA : r == 1 ? pB : r == 2 ? pC : pD;
+                    s_champ[lane] = __ldg(pr + k);
+                }
+                __syncwarp();
+                unsigned long long cvAC[4], cvBD[4];             // champion c at corners (A, C) and (B, D), packed
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 t4 = reinterpret_cast<const float4*>(s_champ)[c];
+                    cvAC[c] = pack2(t4.x, t4.z); cvBD[c] = pack2(t4.y, t4.w);
+                }
+                const unsigned long long MINUS1 = pack2(-1.0f, -1.0f);
+
+                // survivors, ascending category order
+                int n = 0;
+                const int iters = NQ > 0 ? NQ : (p.Q + 31) >> 5;
+#pragma unroll
+                for (int it = 0; it < iters; ++it) {
+                    const int q0 = it * 32, q = q0 + lane;
+                    const bool valid = q < p.Q;
+                    float a, bq, c_, d;
+                    if (NQ > 0) { a = la_[it]; bq = rb_[it]; c_ = lc_[it]; d = rd_[it]; }
+                    else {
+                        a = bq = c_ = d = 0.f;
+                        if (valid) { a = __ldg(pA + q); bq = __ldg(pB + q); c_ = __ldg(pC + q); d = __ldg(pD + q); }
+                    }
+                    bool dom = false;
+                    const unsigned long long ac = pack2(a, c_), bd = pack2(bq, d);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (use[c]) {                              // warp-uniform
+                            // smallest of the champion's four leads over q: RN(champion - q) is >= 0 exactly when champion >= q.
+                            // A champion with a smaller index may tie; one with a larger index (or q itself) must lead by the margin.
+                            float d0, d1, d2, d3;
+                            unpack2(fma2(ac, MINUS1, cvAC[c]), d0, d1);
+                            unpack2(fma2(bd, MINUS1, cvBD[c]), d2, d3);
+                            const float lead = fminf(fminf(d0, d1), fminf(d2, d3));
+                            dom = dom || (lead >= (kk[c] < q ? 0.f : margin));
+                        }
+                    }
+                    const bool keep = valid && !dom;
+                    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                    if (keep) {
+                        const int pos = n + __popc(bal & ((1u << lane) - 1u));
+                        if (pos < p.cap) { s_val[pos] = make_float4(a, c_, bq, d); s_list[pos] = q; }
+                    }
+                    n += __popc(bal);
+                }
+                __syncwarp();
+
+                // evaluate the survivors on 8x8 pixel tiles of the cell: lane = (row lane/8 and +4, column lane%8)
+                for (int ty = ys; ty < ye; ty += 8) {
+                    for (int tx = xs; tx < xe; tx += 8) {
+                        const int X = tx + (lane & 7), Y0 = ty + (lane >> 3), Y1 = Y0 + 4;
+                        const bool okx = X < xe, ok0 = okx && Y0 < ye, ok1 = okx && Y1 < ye;
+                        const float2 lx = s_lx[min(X, p.W - 1)], la = s_ly[min(Y0, p.H - 1)], lb = s_ly[min(Y1, p.H - 1)];
+                        float best0 = -INFINITY, best1 = -INFINITY;
+                        int i0 = 0, i1 = 0;
+                        if (n <= p.cap) {
+                            const unsigned long long LX0 = pack2(lx.x, lx.x), LX1 = pack2(lx.y, lx.y);
+#pragma unroll 2
+                            for (int i = 0; i < n; ++i) {
+                                const float4 v = s_val[i];
+                                float tt, uu;
+                                unpack2(fma2(LX0, pack2(v.x, v.y), mul2(LX1, pack2(v.z, v.w))), tt, uu);   // t = fma(lx0,A,lx1*B), u = fma(lx0,C,lx1*D)
+                                const float v0 = __fmaf_rn(la.x, tt, __fmul_rn(la.y, uu));
+                                const float v1 = __fmaf_rn(lb.x, tt, __fmul_rn(lb.y, uu));
+                                if (v0 > best0) { best0 = v0; i0 = i; }
+                                if (v1 > best1) { best1 = v1; i1 = i; }
+                            }
+                            i0 = s_list[i0]; i1 = s_list[i1];
+                        } else {
+                            // more survivors than slots (incoherent cell of a wide-Q image): every category, taps from global memory
+                            for (int q = 0; q < p.Q; ++q) {
+                                const float tt = lerp_w(lx.x, __ldg(pA + q), lx.y, __ldg(pB + q));
+                                const float uu = lerp_w(lx.x, __ldg(pC + q), lx.y, __ldg(pD + q));
+                                const float v0 = __fmaf_rn(la.x, tt, __fmul_rn(la.y, uu));
+                                const float v1 = __fmaf_rn(lb.x, tt, __fmul_rn(lb.y, uu));
+                                if (v0 > best0) { best0 = v0; i0 = q; }
+                                if (v1 > best1) { best1 = v1; i1 = q; }
+                            }
+                        }
+                        const int tile_off = (ty - ys) * p.W + tx;    // relative to the lane's base pixel
+                        if (lbl_lane) {
+                            if (ok0) lbl_lane[tile_off] = (int16_t)i0;
+                            if (ok1) lbl_lane[tile_off + W4] = (int16_t)i1;
+                        }
+                        if (hist) {
+                            if (ty != ys || tx != xs) {           // later tiles of a large cell: the ground truth was not requested ahead
+                                g0 = ok0 ? gt_lane[tile_off] : (GT)0;
+                                g1 = ok1 ? gt_lane[tile_off + W4] : (GT)0;
+                            }
+                            const int c0 = ok0 ? class_of<GT>(g0, p.n) : -1, c1 = ok1 ? class_of<GT>(g1, p.n) : -1;
+                            warp_hist_add(hist, c0 >= 0 ? c0 * p.n + i0 : -1);
+                            warp_hist_add(hist, c1 >= 0 ? c1 * p.n + i1 : -1);
+                        }
+                    }
+                }
+            }
+            // slide right
+            hA = hB; hC = hD;
+            if (NQ > 0) {
+#pragma unroll
+                for (int it = 0; it < NQ; ++it) { la_[it] = rb_[it]; lc_[it] = rd_[it]; }
+            }
+        }
+    }
+    if (p.hist && p.hist_in_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+            const int v = s_hist[i];
+            if (v) atomicAdd(p.hist + i, v);
+        }
+    }
+}
+
+typedef void (*PrunedKernel)(const DecodeParams);
+template <typename GT>
+static PrunedKernel pruned_kernel_for_q(int Q) {
+    const int nq = (Q + 31) / 32;
+    switch (nq) {
+        case 1: return decode_pruned_kernel<GT, 1>;
+        case 2: return decode_pruned_kernel<GT, 2>;
+        case 3: return decode_pruned_kernel<GT, 3>;
+        case 4: return decode_pruned_kernel<GT, 4>;
+        default: return decode_pruned_kernel<GT, 0>;
+    }
+}
+static PrunedKernel pruned_kernel_for(int gt_dtype, int Q) {
+    switch (gt_dtype) {
+        case ZUTIS_GT_U8: return pruned_kernel_for_q<uint8_t>(Q);
+        case ZUTIS_GT_I16: return pruned_kernel_for_q<int16_t>(Q);
+        case ZUTIS_GT_I32: return pruned_kernel_for_q<int32_t>(Q);
+        default: return pruned_kernel_for_q<long long>(Q);
     }
 }
 
@@ -706,12 +1073,24 @@ int launch_threshold_tiled(const float* probs, long sb, long sq, long sy, long s
 
 using namespace zutis;
 
-extern "C" int zutis_decode_score(const float* logits, long sb, long sq, long sy, long sx,
-                                  int B, int Q, int h, int w, int H, int W,
-                                  const void* gt, int gt_dtype, long gt_sb,
-                                  int16_t* labels, int32_t* hist_partial, int n_classes,
-                                  int mode, void* stream_) {
+// workspace of the pruned path: champions [B*h*w] int2 | per-image counters [2*B] int
+static size_t decode_workspace_bytes(int B, int h, int w) { return decode_ws_bytes(B, (long)h * w); }
+
+extern "C" size_t zutis_decode_workspace_bytes(int B, int Q, int h, int w, int H, int W) {
+    (void)Q; (void)H; (void)W;
+    if (B <= 0 || h <= 0 || w <= 0) return 0;
+    return decode_workspace_bytes(B, h, w);
+}
+
+static int decode_score_impl(const float* logits, long sb, long sq, long sy, long sx,
+                             int B, int Q, int h, int w, int H, int W,
+                             const void* gt, int gt_dtype, long gt_sb,
+                             int16_t* labels, int32_t* hist_partial, int n_classes,
+                             int mode, void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    // the contraction may have left the champions in the workspace already (zutis_gemm_logits_champions)
+    const bool champions_ready = (mode & ZUTIS_DECODE_CHAMPIONS_READY) != 0;
+    mode &= ~ZUTIS_DECODE_CHAMPIONS_READY;
     ZUTIS_REQUIRE(logits != nullptr, "zutis_decode_score: logits is NULL");
     ZUTIS_REQUIRE(B > 0 && Q > 0 && h > 0 && w > 0 && H > 0 && W > 0,
                   "zutis_decode_score: non-positive shape B=%d Q=%d h=%d w=%d H=%d W=%d", B, Q, h, w, H, W);
@@ -736,6 +1115,7 @@ extern "C" int zutis_decode_score(const float* logits, long sb, long sq, long sy
     p.labels = labels; p.hist = hist_partial; p.n = hist_partial ? n_classes : 1;
     p.identity = (H == h && W == w);
     p.XB = (W + 31) / 32; p.XR = 0; p.QC = 0; p.QS = 0; p.hist_in_smem = 0; p.n_items = 0; p.n_groups = 0; p.vec_stage = 0; p.gt_bytes = gt ? gt_dtype_bytes(gt_dtype) : 0;
+    p.select = 0; p.agree_min = 0; p.img_stats = nullptr; p.champ = nullptr; p.cap = 0; p.off_warp = 0;
 
     const int sms = sm_count();
 
@@ -753,9 +1133,17 @@ extern "C" int zutis_decode_score(const float* logits, long sb, long sq, long sy
     }
     if (mode == ZUTIS_DECODE_TILED && !tiled_ok)
         return fail(ZUTIS_ERR_UNSUPPORTED, "zutis_decode_score: tiled kernel needs up-sampling with <= 8 low-res columns per 32 outputs");
-    if (mode == ZUTIS_DECODE_PRUNED)
-        return fail(ZUTIS_ERR_UNSUPPORTED, "zutis_decode_score: pruned kernel not built yet");
-    const bool use_tiled = (mode == ZUTIS_DECODE_TILED) || (mode == ZUTIS_DECODE_AUTO && tiled_ok);
+    // ---- can the pruned kernel take the coherent images?  (category index contiguous, cells of >= 4x4 pixels, workspace)
+    const size_t ws_need = decode_workspace_bytes(B, h, w);
+    const long extent_px = (long)(h - 1) * sy + (long)(w - 1) * sx + (long)(Q - 1);
+    bool pruned_ok = tiled_ok && sq == 1 && sx > 0 && sy > 0 && H >= 4 * h && W >= 4 * w && Q >= 8 && B <= 1024 &&
+                     extent_px < 2147483647L && (long)B * h * w < 2147483647L && workspace != nullptr && workspace_bytes >= ws_need &&
+                     (reinterpret_cast<uintptr_t>(workspace) & 7) == 0 && w <= 8192 &&
+                     (sx & 3) == 0 && (sy & 3) == 0 && (sb & 3) == 0 && sx >= ((Q + 3) & ~3) && (reinterpret_cast<uintptr_t>(logits) & 15) == 0;
+    if (mode == ZUTIS_DECODE_PRUNED && !pruned_ok)
+        return fail(ZUTIS_ERR_UNSUPPORTED, "zutis_decode_score: pruned kernel needs contiguous categories, >= 4x up-sampling, B <= 1024 and a workspace of %zu bytes (zutis_decode_workspace_bytes)", ws_need);
+    const bool use_pruned = pruned_ok && (mode == ZUTIS_DECODE_PRUNED || mode == ZUTIS_DECODE_AUTO);
+    const bool use_tiled = use_pruned || (mode == ZUTIS_DECODE_TILED) || (mode == ZUTIS_DECODE_AUTO && tiled_ok);
 
     if (use_tiled) {
         p.XR = XR;
@@ -780,13 +1168,54 @@ extern "C" int zutis_decode_score(const float* logits, long sb, long sq, long sy
         p.vec_stage = (sq == 1) && ((sx & 3) == 0) && ((sy & 3) == 0) && ((sb & 3) == 0) && (sx >= ((Q + 3) & ~3)) &&
                       ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
         const size_t smem = (size_t)(p.hist_in_smem ? ((nn + 3) & ~3) : 0) * 4 + (size_t)((h + 1 + 3) & ~3) * 4 + (size_t)groups * 16 +
-                            (size_t)((H + 1) & ~1) * 8 + (size_t)kTiledWarps * 2 * 2 * XR * p.QS * 4;
+                            (size_t)((H + 1) & ~1) * 8 + (size_t)kTiledWarps * 2 * 2 * XR * p.QS * 4 + (use_pruned ? (size_t)((B + 3) & ~3) * 4 : 0);
         const long extent = (long)(h - 1) * sy + (long)(w - 1) * sx + (long)(Q - 1) * sq;      // per-image offsets stay 32-bit in the kernel
         if (groups > kMaxGroups || H > kMaxTableRows || smem > 200 * 1024 || extent >= 2147483647L || sx < 0 || sy < 0 || sq < 0 ||
             p.n_items * ((Q + p.QC - 1) / p.QC) >= 2147483647L) {
-            if (mode == ZUTIS_DECODE_TILED)
+            if (mode == ZUTIS_DECODE_TILED || mode == ZUTIS_DECODE_PRUNED)
                 return fail(ZUTIS_ERR_UNSUPPORTED, "zutis_decode_score: tiled kernel does not fit this shape (groups=%d smem=%zu)", groups, smem);
         } else {
+            // ---- pruned path: champions per low-res pixel, then the pruned kernel on the finite + coherent images and the
+            // tiled kernel on the rest (each kernel returns at once when it has no image)
+            size_t psmem = 0;
+            if (use_pruned) {
+                p.cap = Q <= 128 ? ((Q + 3) & ~3) : 256;
+                const size_t tables = (size_t)(p.hist_in_smem ? ((nn + 3) & ~3) : 0) * 4 + (size_t)((h + 1 + 3) & ~3) * 4 + (size_t)((w + 1 + 3) & ~3) * 4 +
+                                      (size_t)((H + 1) & ~1) * 8 + (size_t)((W + 1) & ~1) * 8 + (size_t)((B + 3) & ~3) * 4;
+                p.off_warp = (int)tables;                    // a multiple of 16 bytes
+                psmem = tables + (size_t)kPrunedWarps * p.cap * 20 + (size_t)kPrunedWarps * 64;
+                if (psmem > 100 * 1024) {
+                    if (mode == ZUTIS_DECODE_PRUNED)
+                        return fail(ZUTIS_ERR_UNSUPPORTED, "zutis_decode_score: pruned kernel does not fit this shape (smem=%zu)", psmem);
+                    psmem = 0;                                   // AUTO: plain tiled launch below
+                }
+            }
+            if (psmem) {
+                int2* champ = decode_ws_champ(workspace);
+                int* stats = decode_ws_stats(workspace, B, (long)h * w);
+                if (!champions_ready) {
+                    ZUTIS_CUDA(cudaMemsetAsync(stats, 0, (size_t)2 * B * 4, stream));
+                    champion_kernel<<<(unsigned)(B * h), 256, (size_t)w * 4, stream>>>(logits, sb, sy, sx, B, Q, h, w, champ, stats);
+                    st = check_launch("champion_kernel");
+                    if (st != ZUTIS_OK) return st;
+                }
+                p.champ = champ; p.img_stats = stats;
+                // AUTO: an image is worth pruning when >= 10 % of its horizontally adjacent low-res pixels share their champion
+                // (model outputs: ~30 %; i.i.d. noise: 1 %); PRUNED forces every finite image through the pruned kernel
+                p.agree_min = mode == ZUTIS_DECODE_PRUNED ? 0 : (int)(((long)h * (w - 1) + 9) / 10);
+                p.select = 2;
+                PrunedKernel pk = pruned_kernel_for(hist_partial ? gt_dtype : ZUTIS_GT_I64, Q);
+                ZUTIS_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+                int pper = 1;
+                ZUTIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pper, pk, kPrunedWarps * 32, psmem));
+                if (pper < 1) return fail(ZUTIS_ERR_UNSUPPORTED, "zutis_decode_score: pruned kernel does not fit (smem %zu)", psmem);
+                long pblocks = ((long)B * h * ((w + kCellRun - 1) / kCellRun) + kPrunedWarps - 1) / kPrunedWarps;
+                if (pblocks > (long)sms * pper) pblocks = (long)sms * pper;
+                pk<<<(unsigned)pblocks, kPrunedWarps * 32, psmem, stream>>>(p);
+                st = check_launch("decode_pruned_kernel");
+                if (st != ZUTIS_OK) return st;
+                p.select = 1;
+            }
             ZUTIS_CUDA(cudaFuncSetAttribute(decode_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int per_sm = 1;
             ZUTIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_tiled_kernel, kTiledWarps * 32, smem));
@@ -807,4 +1236,22 @@ extern "C" int zutis_decode_score(const float* logits, long sb, long sq, long sy
         decode_generic_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
         return check_launch("decode_generic_kernel");
     }
+}
+
+extern "C" int zutis_decode_score(const float* logits, long sb, long sq, long sy, long sx,
+                                  int B, int Q, int h, int w, int H, int W,
+                                  const void* gt, int gt_dtype, long gt_sb,
+                                  int16_t* labels, int32_t* hist_partial, int n_classes,
+                                  int mode, void* stream) {
+    return decode_score_impl(logits, sb, sq, sy, sx, B, Q, h, w, H, W, gt, gt_dtype, gt_sb, labels, hist_partial, n_classes, mode,
+                             nullptr, 0, stream);
+}
+
+extern "C" int zutis_decode_score_ws(const float* logits, long sb, long sq, long sy, long sx,
+                                     int B, int Q, int h, int w, int H, int W,
+                                     const void* gt, int gt_dtype, long gt_sb,
+                                     int16_t* labels, int32_t* hist_partial, int n_classes,
+                                     int mode, void* workspace, size_t workspace_bytes, void* stream) {
+    return decode_score_impl(logits, sb, sq, sy, sx, B, Q, h, w, H, W, gt, gt_dtype, gt_sb, labels, hist_partial, n_classes, mode,
+                             workspace, workspace_bytes, stream);
 }

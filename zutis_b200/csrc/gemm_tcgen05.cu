@@ -69,6 +69,9 @@ struct TcParams {
     int a_col0;       // first TMEM column of the per-stage A operand (64 columns per stage: hi | lo)
     int passes;       // 3 = hi*hi + hi*lo + lo*hi, 1 = hi*hi only
     int sigmoid;
+    int2* champ;      // optional: (first-max category, bits of max |logit|) per pixel, for the pruned decode kernel
+    int* img_stats;   // optional: [batch] adjacent-champion agreements | [batch] non-finite flags
+    int img_w;        // low-res image width (pixels per row), for the agreement count
 };
 
 // ------------------------------------------------------------------------------------ PTX helpers
@@ -366,6 +369,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
             float* crow = p.C + (long)b * p.strideC + pix * p.stride_cp;
             const bool vec_ok = (p.stride_cn == 1) && ((p.stride_cp & 3) == 0) && ((p.strideC & 3) == 0) &&
                                 ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+            float ch_best = -INFINITY, ch_amax = 0.f;       // this pixel's champion (p.champ != nullptr: single category tile)
+            int ch_idx = 0x7fffffff;
+            bool ch_bad = false;
             for (int c = 0; c < p.umma_n / 16; ++c) {
                 uint32_t v[16];
                 tmem_ld_x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * p.umma_n + c * 16), v);
@@ -377,6 +383,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
                     for (int j = 0; j < 16; ++j) {
                         f[j] = __uint_as_float(v[j]);
                         if (p.sigmoid) f[j] = sigmoidf_exact(f[j]);
+                    }
+                    if (p.champ) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (n0 + j < p.M) {
+                                const float af = fabsf(f[j]);
+                                ch_bad = ch_bad || !(af <= 3.402823466e38f);
+                                ch_amax = fmaxf(ch_amax, af);
+                                if (f[j] > ch_best || ch_idx == 0x7fffffff) { ch_best = f[j]; ch_idx = n0 + j; }
+                            }
+                        }
                     }
                     if (vec_ok) {
                         // pixel-major rows: padding columns up to the row pitch hold zeros (zero-padded operand rows)
@@ -399,6 +416,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tmem_empty(a));
+            if (p.champ) {
+                if (row_ok) p.champ[(long)b * p.N + pix] = make_int2(ch_idx, __float_as_int(ch_amax));
+                // neighbours inside the warp only (1 pair in 32 is not counted: the count feeds a coarse threshold)
+                const int right = __shfl_down_sync(0xffffffffu, ch_idx, 1);
+                const bool pair = row_ok && lane < 31 && pix + 1 < p.N && ((pix + 1) % p.img_w) != 0 && right == ch_idx;
+                const int agree = __popc(__ballot_sync(0xffffffffu, pair));
+                const bool bad = __any_sync(0xffffffffu, ch_bad && row_ok);
+                if (lane == 0) {
+                    if (agree) atomicAdd(p.img_stats + b, agree);
+                    if (bad) atomicOr(p.img_stats + p.batch + b, 1);
+                }
+            }
         }
     } else if (warp >= 8) {
         // =============================== converters ===============================
@@ -532,6 +561,10 @@ size_t gemm_tcgen05_workspace_bytes(int M, long, int K, int batch, int) {
     return (size_t)2 * batch * pl.rows_per_image * K * 4;
 }
 
+bool gemm_tcgen05_makes_champions(const GemmParams& g) {
+    return g.champ && g.img_stats && g.img_w > 0 && make_plan(g.M).n_tiles == 1 && !g.sigmoid;
+}
+
 bool gemm_tcgen05_supports(const GemmParams& g, int batch, int flags) {
     if ((flags & ZUTIS_GEMM_PRECISION_MASK) == ZUTIS_GEMM_FP32_SIMT) return false;
     if (g.K % BLOCK_K != 0 || g.M > 1024) return false;
@@ -581,7 +614,11 @@ int launch_gemm_tcgen05(const GemmParams& g, int batch, int flags, void* workspa
     p.sa = pl.sa; p.sb = pl.sb; p.st = pl.st; p.b_slot_bytes = pl.b_slot_bytes; p.tmem_cols = pl.tmem_cols; p.acc_bufs = pl.acc_bufs; p.a_col0 = pl.a_col0;
     p.passes = ((flags & ZUTIS_GEMM_PRECISION_MASK) == ZUTIS_GEMM_TF32X3) ? 3 : 1;
     p.sigmoid = g.sigmoid;
+    // the champion by-product needs every category of a pixel in one thread: single category tile, raw logits
+    const bool champs = g.champ && g.img_stats && g.img_w > 0 && pl.n_tiles == 1 && !g.sigmoid;
+    p.champ = champs ? g.champ : nullptr; p.img_stats = champs ? g.img_stats : nullptr; p.img_w = g.img_w;
 
+    if (champs) ZUTIS_CUDA(cudaMemsetAsync(g.img_stats, 0, (size_t)2 * batch * sizeof(int), stream));
     const size_t smem = pl.smem;
     ZUTIS_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long total_tiles = (long)batch * p.p_tiles * p.n_tiles;

@@ -258,8 +258,11 @@ def decode_and_score(text: torch.Tensor, patch_tokens: torch.Tensor, label_trues
     Equivalent to ``meter.update(label_trues, predict(..., "semantic", size=size))``
     (trainer.py:331-347) without materialising logits or labels on the host.
     """
-    lowres = ops.contraction(text, patch_tokens, precision=precision)
-    return meter.update_from_logits(lowres, label_trues, size=size, want_labels=want_labels)
+    # the contraction's epilogue also leaves the per-pixel champions the pruning decode kernel needs in `ws`
+    ws = meter.__dict__.setdefault("_decode_ws", ops.DecodeWorkspace())
+    cache = meter.__dict__.setdefault("_text_cache", {})
+    lowres = ops.contraction(text, patch_tokens, precision=precision, a_cache=cache, decode_ws=ws)
+    return meter.update_from_logits(lowres, label_trues, size=size, want_labels=want_labels, workspace=ws)
 
 
 class ZutisDecoder:

@@ -8,6 +8,8 @@ from __future__ import annotations
 
 from typing import Optional, Tuple
 
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -49,8 +51,26 @@ def gemm_flags(precision: Optional[str], sigmoid: bool = False) -> int:
     return _PRECISIONS[p] | (F.GEMM_SIGMOID if sigmoid else 0)
 
 
+class DecodeWorkspace:
+    """Device scratch of the candidate-pruning decode kernel (champion per low-res pixel, per-image counters).
+
+    Pass the same object to ``contraction(..., decode_ws=ws)`` and ``decode_score(..., workspace=ws)``: the tensor-core
+    contraction then fills it in its epilogue and the decode call skips its own champion pass."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+        self.ready_for: Optional[tuple] = None      # (logits data_ptr, shape) the champions in ``buf`` belong to
+
+    def ensure(self, nbytes: int, device) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(max(nbytes, 8), device=device, dtype=torch.uint8)
+            self.ready_for = None
+        return self.buf
+
+
 def contraction(a: torch.Tensor, feats: torch.Tensor, *, precision: Optional[str] = None, sigmoid: bool = False,
-                pixel_major: bool = True, a_cache: Optional[dict] = None) -> torch.Tensor:
+                pixel_major: bool = True, a_cache: Optional[dict] = None,
+                decode_ws: Optional[DecodeWorkspace] = None) -> torch.Tensor:
     """out[b,n,y,x] = act(sum_c a[(b,)n,c] * feats[b,y,x,c])   (zutis.py:361-365, :184-186 + :209).
 
     a: [M,C] shared by the batch (text embeddings) or [B,M,C] per image (queries).
@@ -104,10 +124,23 @@ def contraction(a: torch.Tensor, feats: torch.Tensor, *, precision: Optional[str
         elif ws_bytes:
             ws = torch.empty(ws_bytes, device=feats.device, dtype=torch.uint8)
         with torch.cuda.device(feats.device):
-            F.call("zutis_gemm_logits", a.data_ptr(), a.stride(-2), 0 if shared else a.stride(0),
-                   feats.data_ptr(), feats.stride(2), feats.stride(0),
-                   buf.data_ptr(), s_cn, s_cp, s_c, M, N, Cc, B, fl,
-                   ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
+            if decode_ws is not None and pixel_major and not sigmoid:
+                dws_bytes = F.lib().zutis_decode_workspace_bytes(B, M, h, w, h, w)
+                dws = decode_ws.ensure(dws_bytes, feats.device)
+                written = C.c_int(0)
+                decode_ws.ready_for = None
+                F.call("zutis_gemm_logits_champions", a.data_ptr(), a.stride(-2), 0 if shared else a.stride(0),
+                       feats.data_ptr(), feats.stride(2), feats.stride(0),
+                       buf.data_ptr(), s_cn, s_cp, s_c, M, N, Cc, B, fl,
+                       ws.data_ptr() if ws is not None else None, ws_bytes,
+                       w, dws.data_ptr(), dws_bytes, C.addressof(written), _stream())
+                if written.value:
+                    decode_ws.ready_for = (buf.data_ptr(), (B, M, h, w))
+            else:
+                F.call("zutis_gemm_logits", a.data_ptr(), a.stride(-2), 0 if shared else a.stride(0),
+                       feats.data_ptr(), feats.stride(2), feats.stride(0),
+                       buf.data_ptr(), s_cn, s_cp, s_c, M, N, Cc, B, fl,
+                       ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
 
     if (precision or DEFAULT_PRECISION) == "auto":
         try:
@@ -121,7 +154,8 @@ def contraction(a: torch.Tensor, feats: torch.Tensor, *, precision: Optional[str
 
 def decode_score(logits: torch.Tensor, size=None, *, gt: Optional[torch.Tensor] = None,
                  hist_partial: Optional[torch.Tensor] = None, n_classes: Optional[int] = None,
-                 want_labels: bool = True, mode: int = F.DECODE_AUTO) -> Optional[torch.Tensor]:
+                 want_labels: bool = True, mode: int = F.DECODE_AUTO,
+                 workspace: Optional[DecodeWorkspace] = None) -> Optional[torch.Tensor]:
     """Fused upsample -> argmax -> (labels, confusion counts)   (zutis.py:366-372 + running_score.py:10-16).
 
     logits [B,Q,h,w] fp32 with any strides; gt [B,H,W] integer CUDA tensor (or None);
@@ -150,11 +184,21 @@ def decode_score(logits: torch.Tensor, size=None, *, gt: Optional[torch.Tensor] 
         if hist_partial.dtype != torch.int32 or hist_partial.numel() != n_classes * n_classes or not hist_partial.is_contiguous():
             raise ValueError("hist_partial must be a contiguous int32 tensor with n_classes^2 elements")
     with torch.cuda.device(logits.device):
-        F.call("zutis_decode_score", logits.data_ptr(), logits.stride(0), logits.stride(1), logits.stride(2), logits.stride(3),
+        # scratch for the candidate-pruning kernel (champion per low-res pixel); the library ignores it when the
+        # shape or the strides rule that kernel out
+        ws_bytes = F.lib().zutis_decode_workspace_bytes(B, Q, h, w, H, W)
+        if workspace is not None:
+            ws = workspace.ensure(ws_bytes, logits.device)
+            if workspace.ready_for == (logits.data_ptr(), (B, Q, h, w)):
+                mode |= F.DECODE_CHAMPIONS_READY             # the contraction's epilogue already filled it for these logits
+            workspace.ready_for = None
+        else:
+            ws = torch.empty(max(ws_bytes, 8), device=logits.device, dtype=torch.uint8)
+        F.call("zutis_decode_score_ws", logits.data_ptr(), logits.stride(0), logits.stride(1), logits.stride(2), logits.stride(3),
                B, Q, h, w, H, W, gt_ptr, gt_code, gt_sb,
                labels.data_ptr() if labels is not None else None,
                hist_partial.data_ptr() if hist_partial is not None else None,
-               n_classes if hist_partial is not None else 0, mode, _stream())
+               n_classes if hist_partial is not None else 0, mode, ws.data_ptr(), ws_bytes, _stream())
     return labels
 
 

@@ -92,7 +92,8 @@ class RunningScore(object):
             ops.score_labels(t, p, self._partial, self.n_classes)
             self._note_pixels(t.numel())
 
-    def update_from_logits(self, lowres_logits: torch.Tensor, label_trues, size=None, want_labels: bool = False):
+    def update_from_logits(self, lowres_logits: torch.Tensor, label_trues, size=None, want_labels: bool = False,
+                           workspace=None):
         """Fused path: upsample + argmax + count in one kernel; full-resolution logits never exist.
 
         Equivalent to ``update(label_trues, argmax(interpolate(lowres_logits, size)))``
@@ -100,7 +101,7 @@ class RunningScore(object):
         """
         gt = self._as_device_labels(label_trues)
         labels = ops.decode_score(lowres_logits, size, gt=gt, hist_partial=self._partial, n_classes=self.n_classes,
-                                  want_labels=want_labels)
+                                  want_labels=want_labels, workspace=workspace)
         self._note_pixels(gt.numel())
         return labels
 

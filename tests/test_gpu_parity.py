@@ -272,19 +272,22 @@ def test_contraction_epilogue_champions_equal_decode_prepass(zb):
     ws = zb.ops.DecodeWorkspace()
     lo = zb.ops.contraction(text, tokens, precision="tf32x3", decode_ws=ws)
     assert ws.ready_for == (lo.data_ptr(), (B, Q, h, w))
-    n = B * h * w
-    champ_gemm = ws.buf[: n * 8].view(torch.int32).view(n, 2).clone()
-    stats_gemm = ws.buf[n * 8: n * 8 + 8 * B].view(torch.int32).clone()
+    n = B * h * w                                                   # workspace: champions [n] int32 | counters [3*B] int32
+    assert n % 2 == 0
+    champ_gemm = ws.buf[: n * 4].view(torch.int32).clone()
+    stats_gemm = ws.buf[n * 4: n * 4 + 12 * B].view(torch.int32).clone()
     part = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
     got = zb.ops.decode_score(lo, (H, W), gt=gt, hist_partial=part, workspace=ws)                      # READY path
     ws2 = zb.ops.DecodeWorkspace()
     part2 = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
     got2 = zb.ops.decode_score(lo, (H, W), gt=gt, hist_partial=part2, workspace=ws2)                   # own pre-pass
-    champ_own = ws2.buf[: n * 8].view(torch.int32).view(n, 2)
-    stats_own = ws2.buf[n * 8: n * 8 + 8 * B].view(torch.int32)
-    finite = (stats_own[B:] == 0).repeat_interleave(h * w)
+    champ_own = ws2.buf[: n * 4].view(torch.int32)
+    stats_own = ws2.buf[n * 4: n * 4 + 12 * B].view(torch.int32)
+    finite = (stats_own[B:2 * B] == 0).repeat_interleave(h * w)
     assert torch.equal(champ_gemm[finite], champ_own[finite])
-    assert torch.equal(stats_gemm[B:] != 0, stats_own[B:] != 0) and stats_own[B:].tolist() == [0, 0, 0, 0, 1]
+    assert torch.equal(stats_gemm[B:2 * B] != 0, stats_own[B:2 * B] != 0) and stats_own[B:2 * B].tolist() == [0, 0, 0, 0, 1]
+    assert torch.equal(stats_gemm[2 * B:3 * B - 1], stats_own[2 * B:3 * B - 1])                      # bits of max |logit| per finite image
+    assert torch.equal(stats_own[2 * B:3 * B - 1].view(torch.float32), lo[:4].abs().amax(dim=(1, 2, 3)))
     thr = (h * (w - 1) + 9) // 10
     assert torch.equal(stats_gemm[:B] >= thr, stats_own[:B] >= thr) and (stats_own[:4] >= thr).tolist() == [True, True, True, False]
     ref_part = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")

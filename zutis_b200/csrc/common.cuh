@@ -109,10 +109,12 @@ __device__ __forceinline__ void warp_hist_add(int* hist, int key) {
 }
 #endif
 
-// workspace of the pruned decode path (zutis_decode_workspace_bytes): champions [B*h*w] int2 | per-image counters [2*B] int
-inline size_t decode_ws_bytes(long B, long hw) { return (size_t)B * hw * 8 + (size_t)2 * B * 4; }
-inline int2* decode_ws_champ(void* ws) { return reinterpret_cast<int2*>(ws); }
-inline int* decode_ws_stats(void* ws, long B, long hw) { return reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + (size_t)B * hw * 8); }
+// workspace of the pruned decode path (zutis_decode_workspace_bytes):
+//   champions [B*h*w] int (first-max category per low-res pixel) | per-image counters [3*B] int:
+//   adjacent-champion agreements, non-finite flags, bits of max |logit| (non-negative floats order like ints)
+inline size_t decode_ws_bytes(long B, long hw) { return (size_t)((B * hw + 1) & ~1L) * 4 + (size_t)3 * B * 4; }
+inline int* decode_ws_champ(void* ws) { return reinterpret_cast<int*>(ws); }
+inline int* decode_ws_stats(void* ws, long B, long hw) { return reinterpret_cast<int*>(ws) + ((B * hw + 1) & ~1L); }
 
 inline int gt_dtype_bytes(int dtype) {
     switch (dtype) {

@@ -48,8 +48,8 @@ struct DecodeParams {
     // image selection between the tiled and the pruned kernel (workspace path only)
     int select;              // 0: every image; 1: images the pruned kernel does NOT take; 2: images it takes
     int agree_min;           // an image is pruned when it is finite and >= agree_min neighbouring low-res pixels share their champion
-    const int* img_stats;    // [B] neighbour agreements | [B] non-finite flags, written by champion_kernel
-    const int2* champ;       // [B*h*w] (first-max category, bits of max |logit|) per low-res pixel
+    const int* img_stats;    // [B] neighbour agreements | [B] non-finite flags | [B] bits of max |logit|, written by champion_kernel
+    const int* champ;        // [B*h*w] first-max category per low-res pixel
     int cap;                 // candidate slots per warp in the pruned kernel
     int off_warp;            // byte offset of the pruned kernel's per-warp areas in dynamic shared memory
 };
@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const
 // A_k >= A_j, B_k >= B_j, C_k >= C_j and D_k >= D_j then v_k >= v_j at EVERY pixel of the cell, in floating point.
 // Category j can therefore never be the first maximum anywhere in the cell when some k dominates it that way and
 //   * k < j (a tie still goes to k), or
-//   * k > j and the dominance holds with a margin m = 2^-20 * max|logit at the four corners|: the exact difference is
+//   * k > j and the dominance holds with a margin m = 2^-20 * max|logit of the image|: the exact difference is
 //     then >= m * (1 - 2^-22) while three roundings per interpolant move the two values by at most 6 * 2^-24 * max|.|
 //     together, so v_k > v_j strictly.
 // Only the four corner champions (first maxima of the corner pixels, found once per low-res pixel by champion_kernel)
@@ -557,11 +557,11 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const
 constexpr int kPrunedWarps = 8;
 constexpr int kCellRun = 8;
 
-// Per low-res pixel: first-max category and max |logit|; per image: the number of horizontally adjacent pixels that
-// share their champion and a non-finite flag.  One block per (image, low-res row); 8 lanes per pixel read the pixel's
+// Per low-res pixel: first-max category; per image: the number of horizontally adjacent pixels that share their
+// champion, a non-finite flag and max |logit|.  One block per (image, low-res row); 8 lanes per pixel read the pixel's
 // categories as float4 (category index contiguous, 16-byte aligned pixels), 4 pixels per warp at a time.
 __global__ void __launch_bounds__(256) champion_kernel(const float* __restrict__ logits, long sb, long sy, long sx, int B, int Q,
-                                                       int h, int w, int2* __restrict__ champ, int* __restrict__ stats) {
+                                                       int h, int w, int* __restrict__ champ, int* __restrict__ stats) {
     extern __shared__ int s_row[];                            // [w]
     __shared__ int s_agree[8];
     const int b = blockIdx.x / h, y = blockIdx.x % h;
@@ -570,6 +570,7 @@ __global__ void __launch_bounds__(256) champion_kernel(const float* __restrict__
     const float* row = logits + (long)b * sb + (long)y * sy;
     const int chunks = (Q + 3) >> 2;
     bool bad = false;
+    float row_amax = 0.f;
     for (int x0 = warp * 4; x0 < w; x0 += 32) {
         const int x = x0 + grp;
         float best = -INFINITY, amax = 0.f;
@@ -598,13 +599,19 @@ __global__ void __launch_bounds__(256) champion_kernel(const float* __restrict__
             amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
             if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
         }
+        row_amax = fmaxf(row_amax, amax);
         if (sub == 0 && x < w) {
-            champ[((long)b * h + y) * w + x] = make_int2(idx, __float_as_int(amax));
+            champ[((long)b * h + y) * w + x] = idx;
             s_row[x] = idx;
         }
     }
     bad = __any_sync(0xffffffffu, bad);
-    if (bad && lane == 0) atomicOr(stats + B + b, 1);
+    int amax_bits = __float_as_int(row_amax);
+    for (int o = 16; o > 0; o >>= 1) amax_bits = max(amax_bits, __shfl_xor_sync(0xffffffffu, amax_bits, o));
+    if (lane == 0) {
+        if (bad) atomicOr(stats + B + b, 1);
+        atomicMax(stats + 2 * B + b, amax_bits);
+    }
     __syncthreads();
     int agree = 0;
     for (int x = threadIdx.x; x + 1 < w; x += blockDim.x) agree += (s_row[x] == s_row[x + 1]);
@@ -668,8 +675,10 @@ __global__ void __launch_bounds__(kPrunedWarps * 32, 3) decode_pruned_kernel(con
         const int cy1 = min(cy + 1, p.h - 1);
         const float* row0 = p.logits + (long)b * p.sb + cy * sy;      // taps of the cells' upper corners
         const float* row1 = p.logits + (long)b * p.sb + cy1 * sy;     //                    lower corners
-        const int2* ch0 = p.champ + ((size_t)b * p.h + cy) * p.w;
-        const int2* ch1 = p.champ + ((size_t)b * p.h + cy1) * p.w;
+        const int* ch0 = p.champ + ((size_t)b * p.h + cy) * p.w;
+        const int* ch1 = p.champ + ((size_t)b * p.h + cy1) * p.w;
+        // 2^-20 * max|logit of the image|, never 0: a champion must not dominate itself (its differences are exactly 0)
+        const float margin = fmaxf(__int_as_float(p.img_stats[2 * p.B + b]) * 9.5367431640625e-07f, 1e-37f);
         // per-lane bases: lane = (row lane/8 [+4], column lane%8) of an 8x8 pixel tile; category lane (+32, +64, ..) of a tap
         const size_t lane_px = (size_t)(ys + (lane >> 3)) * p.W + (lane & 7);
         int16_t* lbl_lane = p.labels ? p.labels + (size_t)b * p.H * p.W + lane_px : nullptr;
@@ -688,7 +697,9 @@ __global__ void __launch_bounds__(kPrunedWarps * 32, 3) decode_pruned_kernel(con
                 lc_[it] = qv ? __ldg(row1_lane + cx_begin * sx + it * 32) : 0.f;
             }
         }
-        int2 hA = __ldg(ch0 + cx_begin), hC = __ldg(ch1 + cx_begin);
+        // champions of the current cell's four corners; the next cell's right corners are requested one cell ahead
+        int hA = __ldg(ch0 + cx_begin), hC = __ldg(ch1 + cx_begin);
+        int hB = __ldg(ch0 + min(cx_begin + 1, p.w - 1)), hD = __ldg(ch1 + min(cx_begin + 1, p.w - 1));
 
         for (int cx = cx_begin; cx < cx_end; ++cx) {
             const int cx1 = min(cx + 1, p.w - 1);
@@ -697,7 +708,8 @@ __global__ void __launch_bounds__(kPrunedWarps * 32, 3) decode_pruned_kernel(con
             const float* pB = row0 + cx1 * sx;
             const float* pC = row1 + cx * sx;
             const float* pD = row1 + cx1 * sx;
-            const int2 hB = __ldg(ch0 + cx1), hD = __ldg(ch1 + cx1);
+            const int cx2 = min(cx + 2, p.w - 1);
+            const int hBn = __ldg(ch0 + cx2), hDn = __ldg(ch1 + cx2);
             // right corners (they become the next cell's left corners)
             float rb_[NQ > 0 ? NQ : 1], rd_[NQ > 0 ? NQ : 1];
             if (NQ > 0) {
@@ -717,9 +729,7 @@ __global__ void __launch_bounds__(kPrunedWarps * 32, 3) decode_pruned_kernel(con
                 if (okf1) g1 = gt_lane[xs + W4];
             }
             if (xs < xe) {
-                const int kk[4] = {hA.x, hB.x, hC.x, hD.x};
-                // 2^-20 * max|corner logits|, never 0: a champion must not dominate itself (its differences are exactly 0)
-                const float margin = fmaxf(fmaxf(fmaxf(__int_as_float(hA.y), __int_as_float(hB.y)), fmaxf(__int_as_float(hC.y), __int_as_float(hD.y))) * 9.5367431640625e-07f, 1e-37f);
+                const int kk[4] = {hA, hB, hC, hD};
                 const bool use[4] = {true, kk[1] != kk[0], kk[2] != kk[0] && kk[2] != kk[1], kk[3] != kk[0] && kk[3] != kk[1] && kk[3] != kk[2]};
 
                 // the champions' values at the four corners: lane 4c+r fetches corner r of champion c
@@ -826,7 +836,7 @@ __global__ void __launch_bounds__(kPrunedWarps * 32, 3) decode_pruned_kernel(con
                 }
             }
             // slide right
-            hA = hB; hC = hD;
+            hA = hB; hC = hD; hB = hBn; hD = hDn;
             if (NQ > 0) {
 #pragma unroll
                 for (int it = 0; it < NQ; ++it) { la_[it] = rb_[it]; lc_[it] = rd_[it]; }
@@ -1191,10 +1201,10 @@ static int decode_score_impl(const float* logits, long sb, long sq, long sy, lon
                 }
             }
             if (psmem) {
-                int2* champ = decode_ws_champ(workspace);
+                int* champ = decode_ws_champ(workspace);
                 int* stats = decode_ws_stats(workspace, B, (long)h * w);
                 if (!champions_ready) {
-                    ZUTIS_CUDA(cudaMemsetAsync(stats, 0, (size_t)2 * B * 4, stream));
+                    ZUTIS_CUDA(cudaMemsetAsync(stats, 0, (size_t)3 * B * 4, stream));
                     champion_kernel<<<(unsigned)(B * h), 256, (size_t)w * 4, stream>>>(logits, sb, sy, sx, B, Q, h, w, champ, stats);
                     st = check_launch("champion_kernel");
                     if (st != ZUTIS_OK) return st;

@@ -10,9 +10,9 @@ struct GemmParams {
     const float* Bm; long ldb, strideB;
     float* C; long stride_cn, stride_cp, strideC;
     int M; long N; int K; int sigmoid;
-    // optional by-product for the pruned decode kernel (zutis_gemm_logits_champions): per pixel the first-max category
-    // and max |logit|, per image the champion agreements of horizontally adjacent pixels and a non-finite flag
-    int2* champ; int* img_stats; int img_w;
+    // optional by-product for the pruned decode kernel (zutis_gemm_logits_champions): per pixel the first-max category,
+    // per image the champion agreements of horizontally adjacent pixels, a non-finite flag and max |logit|
+    int* champ; int* img_stats; int img_w;
 };
 
 #ifdef __CUDACC__

@@ -69,8 +69,8 @@ struct TcParams {
     int a_col0;       // first TMEM column of the per-stage A operand (64 columns per stage: hi | lo)
     int passes;       // 3 = hi*hi + hi*lo + lo*hi, 1 = hi*hi only
     int sigmoid;
-    int2* champ;      // optional: (first-max category, bits of max |logit|) per pixel, for the pruned decode kernel
-    int* img_stats;   // optional: [batch] adjacent-champion agreements | [batch] non-finite flags
+    int* champ;       // optional: first-max category per pixel, for the pruned decode kernel
+    int* img_stats;   // optional: [batch] adjacent-champion agreements | [batch] non-finite flags | [batch] bits of max |logit|
     int img_w;        // low-res image width (pixels per row), for the agreement count
 };
 
@@ -417,15 +417,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tmem_empty(a));
             if (p.champ) {
-                if (row_ok) p.champ[(long)b * p.N + pix] = make_int2(ch_idx, __float_as_int(ch_amax));
+                if (row_ok) p.champ[(long)b * p.N + pix] = ch_idx;
                 // neighbours inside the warp only (1 pair in 32 is not counted: the count feeds a coarse threshold)
                 const int right = __shfl_down_sync(0xffffffffu, ch_idx, 1);
                 const bool pair = row_ok && lane < 31 && pix + 1 < p.N && ((pix + 1) % p.img_w) != 0 && right == ch_idx;
                 const int agree = __popc(__ballot_sync(0xffffffffu, pair));
                 const bool bad = __any_sync(0xffffffffu, ch_bad && row_ok);
+                int amax_bits = row_ok ? __float_as_int(ch_amax) : 0;
+                for (int o = 16; o > 0; o >>= 1) amax_bits = max(amax_bits, __shfl_xor_sync(0xffffffffu, amax_bits, o));
                 if (lane == 0) {
                     if (agree) atomicAdd(p.img_stats + b, agree);
                     if (bad) atomicOr(p.img_stats + p.batch + b, 1);
+                    atomicMax(p.img_stats + 2 * p.batch + b, amax_bits);
                 }
             }
         }
@@ -618,7 +621,7 @@ int launch_gemm_tcgen05(const GemmParams& g, int batch, int flags, void* workspa
     const bool champs = g.champ && g.img_stats && g.img_w > 0 && pl.n_tiles == 1 && !g.sigmoid;
     p.champ = champs ? g.champ : nullptr; p.img_stats = champs ? g.img_stats : nullptr; p.img_w = g.img_w;
 
-    if (champs) ZUTIS_CUDA(cudaMemsetAsync(g.img_stats, 0, (size_t)2 * batch * sizeof(int), stream));
+    if (champs) ZUTIS_CUDA(cudaMemsetAsync(g.img_stats, 0, (size_t)3 * batch * sizeof(int), stream));
     const size_t smem = pl.smem;
     ZUTIS_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long total_tiles = (long)batch * p.p_tiles * p.n_tiles;

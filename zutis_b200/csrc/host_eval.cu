@@ -30,6 +30,7 @@ struct Lane {
     float* logits = nullptr;
     int16_t* labels = nullptr;
     int32_t* partial = nullptr;
+    void* decode_ws = nullptr;       // champions of the pruning decode kernel, filled by the contraction's epilogue
 };
 
 }  // namespace
@@ -62,6 +63,7 @@ extern "C" int zutis_semantic_eval_host(const float* text, const float* tokens, 
     long long* d_hist = nullptr;
     void* d_ws = nullptr;
     const size_t ws_bytes = zutis_gemm_workspace_bytes(Q, hw, D, (int)chunk, gemm_flags);
+    const size_t dws_bytes = zutis_decode_workspace_bytes((int)chunk, Q, h, w, H, W);
     int rc = ZUTIS_OK;
     auto guard = [&](int s) { if (rc == ZUTIS_OK && s != ZUTIS_OK) rc = s; return rc == ZUTIS_OK; };
 
@@ -72,6 +74,7 @@ extern "C" int zutis_semantic_eval_host(const float* text, const float* tokens, 
         guard(check_cuda(cudaMallocAsync((void**)&L.logits, (size_t)chunk * hw * Qp * 4, L.stream), "cudaMallocAsync logits"));
         if (gt) guard(check_cuda(cudaMallocAsync(&L.gt, (size_t)chunk * HW * gt_bytes, L.stream), "cudaMallocAsync gt"));
         if (labels_host) guard(check_cuda(cudaMallocAsync((void**)&L.labels, (size_t)chunk * HW * 2, L.stream), "cudaMallocAsync labels"));
+        guard(check_cuda(cudaMallocAsync(&L.decode_ws, dws_bytes, L.stream), "cudaMallocAsync decode workspace"));
         if (hist_host) {
             guard(check_cuda(cudaMallocAsync((void**)&L.partial, (size_t)n2 * 4, L.stream), "cudaMallocAsync partial"));
             if (rc == ZUTIS_OK) guard(check_cuda(cudaMemsetAsync(L.partial, 0, (size_t)n2 * 4, L.stream), "cudaMemsetAsync"));
@@ -96,11 +99,14 @@ extern "C" int zutis_semantic_eval_host(const float* text, const float* tokens, 
         if (gt && rc == ZUTIS_OK)
             guard(check_cuda(cudaMemcpyAsync(L.gt, (const char*)gt + (size_t)b0 * HW * gt_bytes, (size_t)nb * HW * gt_bytes, cudaMemcpyHostToDevice, L.stream), "H2D gt"));
         if (rc != ZUTIS_OK) break;
-        guard(zutis_gemm_logits(d_text, D, 0, L.tokens, D, hw * D, L.logits, 1, Qp, hw * Qp, Q, hw, D, nb, gemm_flags,
-                                d_ws ? (char*)d_ws + ws_bytes * (it % nlanes) : nullptr, ws_bytes, L.stream));
+        int champions = 0;
+        guard(zutis_gemm_logits_champions(d_text, D, 0, L.tokens, D, hw * D, L.logits, 1, Qp, hw * Qp, Q, hw, D, nb, gemm_flags,
+                                          d_ws ? (char*)d_ws + ws_bytes * (it % nlanes) : nullptr, ws_bytes,
+                                          w, L.decode_ws, dws_bytes, &champions, L.stream));
         if (rc != ZUTIS_OK) break;
-        guard(zutis_decode_score(L.logits, hw * Qp, 1, (long)w * Qp, Qp, nb, Q, h, w, H, W, L.gt, gt_dtype, HW,
-                                 L.labels, hist_host ? L.partial : nullptr, Q, ZUTIS_DECODE_AUTO, L.stream));
+        guard(zutis_decode_score_ws(L.logits, hw * Qp, 1, (long)w * Qp, Qp, nb, Q, h, w, H, W, L.gt, gt_dtype, HW,
+                                    L.labels, hist_host ? L.partial : nullptr, Q,
+                                    ZUTIS_DECODE_AUTO | (champions ? ZUTIS_DECODE_CHAMPIONS_READY : 0), L.decode_ws, dws_bytes, L.stream));
         if (labels_host && rc == ZUTIS_OK)
             guard(check_cuda(cudaMemcpyAsync(labels_host + (size_t)b0 * HW, L.labels, (size_t)nb * HW * 2, cudaMemcpyDeviceToHost, L.stream), "D2H labels"));
     }
@@ -131,6 +137,7 @@ extern "C" int zutis_semantic_eval_host(const float* text, const float* tokens, 
         if (L.gt) cudaFreeAsync(L.gt, L.stream);
         if (L.labels) cudaFreeAsync(L.labels, L.stream);
         if (L.partial) cudaFreeAsync(L.partial, L.stream);
+        if (L.decode_ws) cudaFreeAsync(L.decode_ws, L.stream);
     }
     if (s0) {
         if (d_text) cudaFreeAsync(d_text, s0);

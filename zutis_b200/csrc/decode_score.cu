@@ -48,7 +48,7 @@ struct DecodeParams {
     // image selection between the tiled and the pruned kernel (workspace path only)
     int select;              // 0: every image; 1: images the pruned kernel does NOT take; 2: images it takes
     int agree_min;           // an image is pruned when it is finite and >= agree_min neighbouring low-res pixels share their champion
-    const int* img_stats;    // [B] neighbour agreements | [B] non-finite flags | [B] bits of max |logit|, written by champion_kernel
+    int* img_stats;          // [B] neighbour agreements | [B] non-finite flags | [B] bits of max |logit| (champion_kernel) | work counter
     const int* champ;        // [B*h*w] first-max category per low-res pixel
     int cap;                 // candidate slots per warp in the pruned kernel
     int off_warp;            // byte offset of the pruned kernel's per-warp areas in dynamic shared memory
@@ -292,6 +292,9 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const
 
     // ---- which images are ours (the pruned kernel takes the finite, spatially coherent ones)
     if (p.select) {
+        // this launch follows the pruned kernel on the stream: re-arm its work counter so that the same workspace
+        // (champions included) can serve another decode of the same logits
+        if (blockIdx.x == 0 && threadIdx.x == 0) p.img_stats[3 * p.B] = 0;
         build_image_list(p, p.select == 2, s_img, &s_nimg);
         __syncthreads();
         if (s_nimg == 0) return;
@@ -548,14 +551,14 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const
 // are tried as dominators.  On model-like logits 6 of 81 categories survive per cell (22 of 920); the survivors'
 // corner values are compacted into shared memory and the warp (lane = pixel of an 8x8 tile, 2 pixels per lane) walks
 // only those, in ascending category order with a strict compare = torch.argmax's first maximum.
-// A warp walks a run of kCellRun horizontally adjacent cells: the right corners (B, D) of one cell are the left
+// A warp walks a run of kCellRun horizontally adjacent cells (runs are handed out through an atomic counter): the right corners (B, D) of one cell are the left
 // corners (A, C) of the next and stay in registers (NQ = ceil(Q/32) values per lane and corner, NQ = 0: wide Q, taps
 // re-read per cell).  The ground truth of a cell's first tile is requested before the pruning work so that its
 // latency is hidden.
 // Images with a non-finite logit (NaN ordering) or without spatial coherence (pruning would not pay) are left to the
 // tiled kernel; both kernels derive the same image split from champion_kernel's per-image counters.
 constexpr int kPrunedWarps = 8;
-constexpr int kCellRun = 8;
+constexpr int kCellRun = 4;
 
 // Per low-res pixel: first-max category; per image: the number of horizontally adjacent pixels that share their
 // champion, a non-finite flag and max |logit|.  One block per (image, low-res row); 8 lanes per pixel read the pixel's
@@ -663,7 +666,13 @@ __global__ void __launch_bounds__(kPrunedWarps * 32, 3) decode_pruned_kernel(con
     const unsigned runs_per_row = (unsigned)(p.w + kCellRun - 1) / kCellRun;
     const unsigned runs_per_image = runs_per_row * (unsigned)p.h;
     const unsigned total = (unsigned)s_nimg * runs_per_image;
-    for (unsigned item = blockIdx.x * kPrunedWarps + warp; item < total; item += gridDim.x * kPrunedWarps) {
+    // runs are handed out dynamically (their cost follows the number of survivors): one atomic per run of kCellRun cells
+    unsigned* work_counter = reinterpret_cast<unsigned*>(p.img_stats + 3 * p.B);
+    for (;;) {
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(work_counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= total) break;
         const unsigned slot = item / runs_per_image;
         const unsigned rr = item - slot * runs_per_image;
         const int cy = (int)(rr / runs_per_row);
@@ -1204,7 +1213,7 @@ static int decode_score_impl(const float* logits, long sb, long sq, long sy, lon
                 int* champ = decode_ws_champ(workspace);
                 int* stats = decode_ws_stats(workspace, B, (long)h * w);
                 if (!champions_ready) {
-                    ZUTIS_CUDA(cudaMemsetAsync(stats, 0, (size_t)3 * B * 4, stream));
+                    ZUTIS_CUDA(cudaMemsetAsync(stats, 0, decode_ws_counter_bytes(B), stream));
                     champion_kernel<<<(unsigned)(B * h), 256, (size_t)w * 4, stream>>>(logits, sb, sy, sx, B, Q, h, w, champ, stats);
                     st = check_launch("champion_kernel");
                     if (st != ZUTIS_OK) return st;

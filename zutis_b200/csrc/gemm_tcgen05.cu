@@ -621,7 +621,7 @@ int launch_gemm_tcgen05(const GemmParams& g, int batch, int flags, void* workspa
     const bool champs = g.champ && g.img_stats && g.img_w > 0 && pl.n_tiles == 1 && !g.sigmoid;
     p.champ = champs ? g.champ : nullptr; p.img_stats = champs ? g.img_stats : nullptr; p.img_w = g.img_w;
 
-    if (champs) ZUTIS_CUDA(cudaMemsetAsync(g.img_stats, 0, (size_t)3 * batch * sizeof(int), stream));
+    if (champs) ZUTIS_CUDA(cudaMemsetAsync(g.img_stats, 0, decode_ws_counter_bytes(batch), stream));
     const size_t smem = pl.smem;
     ZUTIS_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long total_tiles = (long)batch * p.p_tiles * p.n_tiles;

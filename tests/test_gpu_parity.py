@@ -204,7 +204,7 @@ def _smooth_logits(B, Q, h, w, gen, contrast=1.0):
     return (contrast * torch.nn.functional.interpolate(coarse, size=(h, w), mode="bilinear", align_corners=True)).contiguous()
 
 
-@pytest.mark.parametrize("case", ["smooth", "smooth_noninteger", "x16", "x6", "iid", "ties", "nonfinite_mix", "wide", "hist_only"])
+@pytest.mark.parametrize("case", ["smooth", "smooth_noninteger", "x16", "x6", "iid", "ties", "nonfinite_mix", "wide", "wide_overflow", "hist_only"])
 def test_pruned_kernel_is_exact(zb, case):
     """The candidate-pruning kernel must give the generic kernel's labels and histogram bit for bit -- on coherent
     logits (where it prunes), on noise (where nearly everything survives), on exact ties and duplicated categories
@@ -234,13 +234,15 @@ def test_pruned_kernel_is_exact(zb, case):
         lo[1, 7, 3, 4] = float("nan"); lo[3, 2, 0, 0] = float("inf"); lo[3, 9, 7, 9] = float("-inf")
     elif case == "wide":
         B, Q, h, w, H, W = 1, 920, 7, 8, 56, 64; lo = _smooth_logits(B, Q, h, w, gen, 0.2)
+    elif case == "wide_overflow":                                         # noise: ~390 of 600 categories survive, more than the 256 slots
+        B, Q, h, w, H, W = 1, 600, 5, 6, 40, 48; lo = torch.randn(B, Q, h, w, generator=gen)
     else:
         B, Q, h, w, H, W = 2, 81, 10, 10, 80, 80; lo = _smooth_logits(B, Q, h, w, gen); want_labels = False
     gt = torch.randint(0, Q, (B, H, W), generator=gen); gt[:, :3] = 1000
     t = pixel_major(lo.cuda())
     ref_part = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
     ref = zb.ops.decode_score(t, (H, W), gt=gt.cuda(), hist_partial=ref_part, mode=_ffi.DECODE_GENERIC)
-    if case != "wide":
+    if not case.startswith("wide"):
         assert np.array_equal(ref.cpu().numpy().astype(np.int64), O.c_decode_semantic(lo.numpy(), (H, W)))
     for mode in (_ffi.DECODE_PRUNED, _ffi.DECODE_AUTO):
         part = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
@@ -250,6 +252,15 @@ def test_pruned_kernel_is_exact(zb, case):
         assert torch.equal(part, ref_part), f"{case}: histogram differs in mode {mode}"
         if want_labels:                                                  # labels without a histogram
             assert torch.equal(zb.ops.decode_score(t, (H, W), mode=mode), ref)
+    if case == "smooth":                                                  # every ground-truth storage type (the kernel is templated on it)
+        gt8 = gt.clamp(max=255)
+        for dt in (torch.uint8, torch.int16, torch.int32):
+            g = (gt8 if dt == torch.uint8 else gt).to(dt).cuda()
+            want = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
+            zb.ops.decode_score(t, (H, W), gt=g, hist_partial=want, mode=_ffi.DECODE_GENERIC, want_labels=False)
+            part = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
+            zb.ops.decode_score(t, (H, W), gt=g, hist_partial=part, mode=_ffi.DECODE_PRUNED, want_labels=False)
+            assert torch.equal(part, want), f"histogram differs for {dt}"
     # the pruned kernel needs contiguous categories; a query-major tensor must be refused in forced mode, not mis-read
     with pytest.raises(zb.ZutisUnsupported):
         zb.ops.decode_score(lo.cuda(), (H, W), mode=_ffi.DECODE_PRUNED)

@@ -51,7 +51,9 @@ struct DecodeParams {
     int* img_stats;          // [B] neighbour agreements | [B] non-finite flags | [B] bits of max |logit| (champion_kernel) | work counter
     const int* champ;        // [B*h*w] first-max category per low-res pixel
     int cap;                 // candidate slots per warp in the pruned kernel
-    int off_warp;            // byte offset of the pruned kernel's per-warp areas in dynamic shared memory
+    // byte offsets of the pruned kernel's tables in dynamic shared memory (computed by the host so that the kernel can
+    // re-derive a pointer with one add instead of a chain of size computations when registers run out)
+    int off_ystart, off_xstart, off_ly, off_lx, off_img, off_warp;
 };
 
 __device__ __forceinline__ bool image_is_pruned(const DecodeParams& p, int b) {
@@ -634,16 +636,15 @@ __global__ void __launch_bounds__(kPrunedWarps * 32, 3) decode_pruned_kernel(con
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nn = p.n * p.n;
-    int* s_hist = reinterpret_cast<int*>(smem);
-    const int hist_words = p.hist_in_smem ? ((nn + 3) & ~3) : 0;
-    int* s_ystart = s_hist + hist_words;                                          // [h+1]
-    int* s_xstart = s_ystart + ((p.h + 1 + 3) & ~3);                              // [w+1]
-    float2* s_ly = reinterpret_cast<float2*>(s_xstart + ((p.w + 1 + 3) & ~3));    // [H]
-    float2* s_lx = s_ly + ((p.H + 1) & ~1);                                       // [W]
-    int* s_img = reinterpret_cast<int*>(s_lx + ((p.W + 1) & ~1));                 // [B]
-    // per-warp areas behind the tables (offset computed by the host): survivors' corner values (A, C, B, D), their
-    // categories, the champions' corner values.
-    char* warp_area = reinterpret_cast<char*>(smem) + p.off_warp;
+    char* smem_c = reinterpret_cast<char*>(smem);
+    int* s_hist = reinterpret_cast<int*>(smem);                                   // [n*n] when the histogram fits
+    int* s_ystart = reinterpret_cast<int*>(smem_c + p.off_ystart);                // [h+1] first output row of each cell row
+    int* s_xstart = reinterpret_cast<int*>(smem_c + p.off_xstart);                // [w+1]
+    float2* s_ly = reinterpret_cast<float2*>(smem_c + p.off_ly);                  // [H] (ly0, ly1)
+    float2* s_lx = reinterpret_cast<float2*>(smem_c + p.off_lx);                  // [W] (lx0, lx1)
+    int* s_img = reinterpret_cast<int*>(smem_c + p.off_img);                      // [B] images of this launch
+    // per-warp areas behind the tables: survivors' corner values (A, C, B, D), their categories, the champions' corner values
+    char* warp_area = smem_c + p.off_warp;
     float4* s_val = reinterpret_cast<float4*>(warp_area) + warp * p.cap;
     int* s_list = reinterpret_cast<int*>(warp_area + (size_t)kPrunedWarps * p.cap * 16) + warp * p.cap;
     float* s_champ = reinterpret_cast<float*>(warp_area + (size_t)kPrunedWarps * p.cap * 20) + warp * 16;
@@ -805,17 +806,21 @@ __global__ void __launch_bounds__(kPrunedWarps * 32, 3) decode_pruned_kernel(con
                         int i0 = 0, i1 = 0;
                         if (n <= p.cap) {
                             const unsigned long long LX0 = pack2(lx.x, lx.x), LX1 = pack2(lx.y, lx.y);
+                            // walk the survivor list by shared-memory address (the winner is remembered as an address too)
+                            const uint32_t first = (uint32_t)__cvta_generic_to_shared(s_val), last = first + (uint32_t)n * 16u;
+                            uint32_t w0 = first, w1 = first;
 #pragma unroll 2
-                            for (int i = 0; i < n; ++i) {
-                                const float4 v = s_val[i];
+                            for (uint32_t at = first; at < last; at += 16u) {
+                                float4 v;
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(at));
                                 float tt, uu;
                                 unpack2(fma2(LX0, pack2(v.x, v.y), mul2(LX1, pack2(v.z, v.w))), tt, uu);   // t = fma(lx0,A,lx1*B), u = fma(lx0,C,lx1*D)
                                 const float v0 = __fmaf_rn(la.x, tt, __fmul_rn(la.y, uu));
                                 const float v1 = __fmaf_rn(lb.x, tt, __fmul_rn(lb.y, uu));
-                                if (v0 > best0) { best0 = v0; i0 = i; }
-                                if (v1 > best1) { best1 = v1; i1 = i; }
+                                if (v0 > best0) { best0 = v0; w0 = at; }
+                                if (v1 > best1) { best1 = v1; w1 = at; }
                             }
-                            i0 = s_list[i0]; i1 = s_list[i1];
+                            i0 = s_list[(w0 - first) >> 4]; i1 = s_list[(w1 - first) >> 4];
                         } else {
                             // more survivors than slots (incoherent cell of a wide-Q image): every category, taps from global memory
                             for (int q = 0; q < p.Q; ++q) {
@@ -1134,7 +1139,8 @@ static int decode_score_impl(const float* logits, long sb, long sq, long sy, lon
     p.labels = labels; p.hist = hist_partial; p.n = hist_partial ? n_classes : 1;
     p.identity = (H == h && W == w);
     p.XB = (W + 31) / 32; p.XR = 0; p.QC = 0; p.QS = 0; p.hist_in_smem = 0; p.n_items = 0; p.n_groups = 0; p.vec_stage = 0; p.gt_bytes = gt ? gt_dtype_bytes(gt_dtype) : 0;
-    p.select = 0; p.agree_min = 0; p.img_stats = nullptr; p.champ = nullptr; p.cap = 0; p.off_warp = 0;
+    p.select = 0; p.agree_min = 0; p.img_stats = nullptr; p.champ = nullptr; p.cap = 0;
+    p.off_ystart = p.off_xstart = p.off_ly = p.off_lx = p.off_img = p.off_warp = 0;
 
     const int sms = sm_count();
 
@@ -1199,9 +1205,13 @@ static int decode_score_impl(const float* logits, long sb, long sq, long sy, lon
             size_t psmem = 0;
             if (use_pruned) {
                 p.cap = Q <= 128 ? ((Q + 3) & ~3) : 256;
-                const size_t tables = (size_t)(p.hist_in_smem ? ((nn + 3) & ~3) : 0) * 4 + (size_t)((h + 1 + 3) & ~3) * 4 + (size_t)((w + 1 + 3) & ~3) * 4 +
-                                      (size_t)((H + 1) & ~1) * 8 + (size_t)((W + 1) & ~1) * 8 + (size_t)((B + 3) & ~3) * 4;
-                p.off_warp = (int)tables;                    // a multiple of 16 bytes
+                p.off_ystart = (p.hist_in_smem ? ((nn + 3) & ~3) : 0) * 4;
+                p.off_xstart = p.off_ystart + ((h + 1 + 3) & ~3) * 4;
+                p.off_ly = p.off_xstart + ((w + 1 + 3) & ~3) * 4;
+                p.off_lx = p.off_ly + ((H + 1) & ~1) * 8;
+                p.off_img = p.off_lx + ((W + 1) & ~1) * 8;
+                p.off_warp = p.off_img + ((B + 3) & ~3) * 4;  // every offset is a multiple of 16 bytes
+                const size_t tables = (size_t)p.off_warp;
                 psmem = tables + (size_t)kPrunedWarps * p.cap * 20 + (size_t)kPrunedWarps * 64;
                 if (psmem > 100 * 1024) {
                     if (mode == ZUTIS_DECODE_PRUNED)

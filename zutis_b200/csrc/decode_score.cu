@@ -697,16 +697,6 @@ __global__ void __launch_bounds__(kPrunedWarps * 32, 3) decode_pruned_kernel(con
         const float* row1_lane = row1 + lane;
         const int W4 = 4 * p.W;
 
-        // left corners of the first cell
-        float la_[NQ > 0 ? NQ : 1], lc_[NQ > 0 ? NQ : 1];
-        if (NQ > 0) {
-#pragma unroll
-            for (int it = 0; it < NQ; ++it) {
-                const bool qv = it * 32 + lane < p.Q;
-                la_[it] = qv ? __ldg(row0_lane + cx_begin * sx + it * 32) : 0.f;
-                lc_[it] = qv ? __ldg(row1_lane + cx_begin * sx + it * 32) : 0.f;
-            }
-        }
         // champions of the current cell's four corners; the next cell's right corners are requested one cell ahead
         int hA = __ldg(ch0 + cx_begin), hC = __ldg(ch1 + cx_begin);
         int hB = __ldg(ch0 + min(cx_begin + 1, p.w - 1)), hD = __ldg(ch1 + min(cx_begin + 1, p.w - 1));
@@ -720,12 +710,14 @@ __global__ void __launch_bounds__(kPrunedWarps * 32, 3) decode_pruned_kernel(con
             const float* pD = row1 + cx1 * sx;
             const int cx2 = min(cx + 2, p.w - 1);
             const int hBn = __ldg(ch0 + cx2), hDn = __ldg(ch1 + cx2);
-            // right corners (they become the next cell's left corners)
-            float rb_[NQ > 0 ? NQ : 1], rd_[NQ > 0 ? NQ : 1];
+            // the four corner taps of this lane's categories (the left pair was the previous cell's right pair: L1 hits)
+            float la_[NQ > 0 ? NQ : 1], lc_[NQ > 0 ? NQ : 1], rb_[NQ > 0 ? NQ : 1], rd_[NQ > 0 ? NQ : 1];
             if (NQ > 0) {
 #pragma unroll
                 for (int it = 0; it < NQ; ++it) {
                     const bool qv = it * 32 + lane < p.Q;
+                    la_[it] = qv ? __ldg(row0_lane + cx * sx + it * 32) : 0.f;
+                    lc_[it] = qv ? __ldg(row1_lane + cx * sx + it * 32) : 0.f;
                     rb_[it] = qv ? __ldg(row0_lane + cx1 * sx + it * 32) : 0.f;
                     rd_[it] = qv ? __ldg(row1_lane + cx1 * sx + it * 32) : 0.f;
                 }
@@ -751,12 +743,6 @@ __global__ void __launch_bounds__(kPrunedWarps * 32, 3) decode_pruned_kernel(con
                     s_champ[lane] = __ldg(pr + k);
                 }
                 __syncwarp();
-                unsigned long long cvAC[4], cvBD[4];             // champion c at corners (A, C) and (B, D), packed
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float4 t4 = reinterpret_cast<const float4*>(s_champ)[c];
-                    cvAC[c] = pack2(t4.x, t4.z); cvBD[c] = pack2(t4.y, t4.w);
-                }
                 const unsigned long long MINUS1 = pack2(-1.0f, -1.0f);
 
                 // survivors, ascending category order
@@ -779,9 +765,10 @@ __global__ void __launch_bounds__(kPrunedWarps * 32, 3) decode_pruned_kernel(con
                         if (use[c]) {                              // warp-uniform
                             // smallest of the champion's four leads over q: RN(champion - q) is >= 0 exactly when champion >= q.
                             // A champion with a smaller index may tie; one with a larger index (or q itself) must lead by the margin.
+                            const float4 t4 = reinterpret_cast<const float4*>(s_champ)[c];    // champion c at (A, B, C, D): broadcast read
                             float d0, d1, d2, d3;
-                            unpack2(fma2(ac, MINUS1, cvAC[c]), d0, d1);
-                            unpack2(fma2(bd, MINUS1, cvBD[c]), d2, d3);
+                            unpack2(fma2(ac, MINUS1, pack2(t4.x, t4.z)), d0, d1);
+                            unpack2(fma2(bd, MINUS1, pack2(t4.y, t4.w)), d2, d3);
                             const float lead = fminf(fminf(d0, d1), fminf(d2, d3));
                             dom = dom || (lead >= (kk[c] < q ? 0.f : margin));
                         }
@@ -851,10 +838,6 @@ __global__ void __launch_bounds__(kPrunedWarps * 32, 3) decode_pruned_kernel(con
             }
             // slide right
             hA = hB; hC = hD; hB = hBn; hD = hDn;
-            if (NQ > 0) {
-#pragma unroll
-                for (int it = 0; it < NQ; ++it) { la_[it] = rb_[it]; lc_[it] = rd_[it]; }
-            }
         }
     }
     if (p.hist && p.hist_in_smem) {

@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--iid", action="store_true", help="spatially independent tokens (adversarial for pruning)")
+    ap.add_argument("--segmented", action="store_true",
+                    help="tokens of a trained-model-like output: piecewise-constant label regions + noise (informational; "
+                         "the default stays the random-init model-like field SURVEY 8d specifies)")
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x3", "tf32"])
     ap.add_argument("--decode", default="auto", choices=["auto", "tiled", "pruned", "generic"],
                     help="decode kernel: auto = exact candidate pruning on coherent images, tiled brute force otherwise")
@@ -62,6 +65,10 @@ def parse_args():
 
 
 # ------------------------------------------------------------------------------ synthetic inputs
+def token_mode(args):
+    return "segmented" if args.segmented else bool(args.iid)
+
+
 def make_inputs_torch(cfg, device, seed, iid=False):
     """Model-like synthetic inputs on `device` (torch is input plumbing here, not the measured path)."""
     import torch
@@ -69,7 +76,16 @@ def make_inputs_torch(cfg, device, seed, iid=False):
     B, Q, D, h, w, H, W = (cfg[k] for k in ("B", "Q", "D", "h", "w", "H", "W"))
     gen = torch.Generator(device=device).manual_seed(seed)
     text = F.normalize(torch.randn(Q, D, device=device, generator=gen), dim=-1)
-    if iid:
+    if iid == "segmented":
+        # these tokens are built around the text embeddings, and bench.py scores every rotating input set against the
+        # first set's text: the text must not depend on the set's seed
+        text = F.normalize(torch.randn(Q, D, device=device, generator=torch.Generator(device=device).manual_seed(4242)), dim=-1)
+    if iid == "segmented":
+        # what a trained model emits: each pixel's token is close to the text embedding of its region's category
+        coarse = torch.randint(0, Q, (B, (h + 7) // 8, (w + 7) // 8), device=device, generator=gen)
+        regions = coarse[:, torch.arange(h, device=device) // 8][:, :, torch.arange(w, device=device) // 8]      # 8x8-pixel regions
+        tokens = F.normalize(text[regions] + 0.04 * torch.randn(B, h, w, D, device=device, generator=gen), dim=-1).contiguous()
+    elif iid:
         tokens = F.normalize(torch.randn(B, h, w, D, device=device, generator=gen), dim=-1)
     else:
         coarse = torch.randn(B, D, h // 2, w // 2, device=device, generator=gen)
@@ -199,14 +215,14 @@ def run_reference(args, cfg, rank, world):
     torch.set_num_threads(os.cpu_count() or 1)
     sample = min(16, cfg["B"])
     small = dict(cfg, B=sample)
-    text, tokens, gt = make_inputs_torch(small, "cpu", 0, args.iid)
+    text, tokens, gt = make_inputs_torch(small, "cpu", 0, token_mode(args))
     t0 = time.perf_counter(); cpu_reference_step(text, tokens, gt, small); t_first = time.perf_counter() - t0
     budget = 150.0
     while sample > 1 and (args.steps + args.warmup) * t_first > budget:
         sample = max(1, sample // 2); t_first /= 2
     if sample != small["B"]:
         small = dict(cfg, B=sample)
-        text, tokens, gt = make_inputs_torch(small, "cpu", 0, args.iid)
+        text, tokens, gt = make_inputs_torch(small, "cpu", 0, token_mode(args))
     for _ in range(args.warmup):
         cpu_reference_step(text, tokens, gt, small)
     t0 = time.perf_counter()
@@ -220,7 +236,7 @@ def run_reference(args, cfg, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {cfg['desc']}", "tokens": "iid" if args.iid else "model-like (x2-upsampled coarse features)",
+        "config": {"workload": f"{args.workload}: {cfg['desc']}", "tokens": {True: "iid", False: "model-like (x2-upsampled coarse features)", "segmented": "segmented (piecewise-constant label regions + noise)"}[token_mode(args)],
                    "gt_dtype": "int64", "sample_images_per_step": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -246,7 +262,7 @@ def run_ours(args, cfg, rank, local, world):
     # rotating input sets: each > L2 (tokens alone are B*h*w*D*4 bytes), re-read only every n_sets steps
     tok_bytes = B * h * w * D * 4
     n_sets = max(3, int(np.ceil(3 * 126e6 / tok_bytes)))
-    sets = [make_inputs_torch(cfg, device, 1000 * rank + s, args.iid) for s in range(n_sets)]
+    sets = [make_inputs_torch(cfg, device, 1000 * rank + s, token_mode(args)) for s in range(n_sets)]
     text = sets[0][0]
     meter = zutis_b200.RunningScore(Q, device=device)
     Qp = (Q + 3) & ~3
@@ -380,7 +396,7 @@ def run_ours(args, cfg, rank, local, world):
     bytes_decode = B * (4 * Q * h * w + 8 * H * W + 2 * H * W)
     bytes_gemm = B * (4 * D * h * w + 4 * Q * h * w) + 4 * Q * D
     achieved = bytes_decode / (decode_ms * 1e-3) / 1e9
-    pruned_path = args.decode in ("auto", "pruned") and H >= 4 * h and W >= 4 * w and Q >= 8 and not args.iid
+    pruned_path = args.decode in ("auto", "pruned") and H >= 4 * h and W >= 4 * w and Q >= 8 and token_mode(args) is not True
     kname = "decode_pruned_kernel" if pruned_path else "decode_tiled_kernel"
     # launches per step: contraction + decode (pruned path: champion pre-pass, pruned kernel, tiled kernel for the other images)
     launches_per_step = 1 + ((2 if champs_written.value else 3) if args.decode in ("auto", "pruned") and H >= 4 * h and W >= 4 * w and Q >= 8 else 1)
@@ -388,7 +404,7 @@ def run_ours(args, cfg, rank, local, world):
         "metric": METRIC, "value": world * B * args.steps / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {cfg['desc']}", "tokens": "iid" if args.iid else "model-like (x2-upsampled coarse features)",
+        "config": {"workload": f"{args.workload}: {cfg['desc']}", "tokens": {True: "iid", False: "model-like (x2-upsampled coarse features)", "segmented": "segmented (piecewise-constant label regions + noise)"}[token_mode(args)],
                    "gt_dtype": "int64", "images_per_gpu_per_step": B, "parallelism": f"dp{world} (images sharded, one int64 all-reduce at the end)",
                    "contraction": {0: "fp32 FFMA", 1: "tcgen05 3xTF32", 2: "tcgen05 TF32 single pass"}[flags & 3],
                    "decode": args.decode + (" (exact candidate pruning on finite, coherent images; tiled brute force on the rest)" if args.decode == "auto" else ""),
@@ -405,7 +421,7 @@ def run_ours(args, cfg, rank, local, world):
                   "labels_differing_from_generic_kernel": label_mismatch},
     }
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = time_cpu_baseline(cfg, min(cfg["B"], 64 if cfg["Q"] <= 128 else 2), 3, args.iid)
+        line["cpu_baseline"] = time_cpu_baseline(cfg, min(cfg["B"], 64 if cfg["Q"] <= 128 else 2), 3, token_mode(args))
     print(json.dumps(line), flush=True)
 
 

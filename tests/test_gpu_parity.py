@@ -204,7 +204,7 @@ def _smooth_logits(B, Q, h, w, gen, contrast=1.0):
     return (contrast * torch.nn.functional.interpolate(coarse, size=(h, w), mode="bilinear", align_corners=True)).contiguous()
 
 
-@pytest.mark.parametrize("case", ["smooth", "smooth_noninteger", "x16", "x6", "iid", "ties", "nonfinite_mix", "wide", "wide_overflow", "hist_only"])
+@pytest.mark.parametrize("case", ["smooth", "smooth_noninteger", "x16", "x6", "iid", "ties", "nonfinite_mix", "wide", "wide_overflow", "hist_only", "uniform_regions"])
 def test_pruned_kernel_is_exact(zb, case):
     """The candidate-pruning kernel must give the generic kernel's labels and histogram bit for bit -- on coherent
     logits (where it prunes), on noise (where nearly everything survives), on exact ties and duplicated categories
@@ -232,6 +232,13 @@ def test_pruned_kernel_is_exact(zb, case):
         B, Q, h, w, H, W = 4, 40, 8, 10, 64, 80
         lo = _smooth_logits(B, Q, h, w, gen)
         lo[1, 7, 3, 4] = float("nan"); lo[3, 2, 0, 0] = float("inf"); lo[3, 9, 7, 9] = float("-inf")
+    elif case == "uniform_regions":                                       # big single-category regions: the whole-cell shortcut
+        B, Q, h, w, H, W = 3, 21, 16, 20, 128, 160
+        lo = 0.05 * torch.randn(B, Q, h, w, generator=gen)
+        region = torch.randint(0, Q, (B, 4, 5), generator=gen).repeat_interleave(4, 1).repeat_interleave(4, 2)
+        lo.scatter_add_(1, region[:, None], torch.ones(B, 1, h, w))
+        lo[1, 3] = lo[1, 7]                                               # a duplicated category inside the uniform regions
+        lo[2, :, :8] = 0.25                                               # a region where every category ties exactly: label 0
     elif case == "wide":
         B, Q, h, w, H, W = 1, 920, 7, 8, 56, 64; lo = _smooth_logits(B, Q, h, w, gen, 0.2)
     elif case == "wide_overflow":                                         # noise: ~390 of 600 categories survive, more than the 256 slots
@@ -283,19 +290,26 @@ def test_contraction_epilogue_champions_equal_decode_prepass(zb):
     ws = zb.ops.DecodeWorkspace()
     lo = zb.ops.contraction(text, tokens, precision="tf32x3", decode_ws=ws)
     assert ws.ready_for == (lo.data_ptr(), (B, Q, h, w))
-    n = B * h * w                                                   # workspace: champions [n] int32 | counters [3*B] int32
+    n = B * h * w                                                   # workspace: champions [n] int32 | leads [n] fp32 | counters [3*B] int32
     assert n % 2 == 0
     champ_gemm = ws.buf[: n * 4].view(torch.int32).clone()
-    stats_gemm = ws.buf[n * 4: n * 4 + 12 * B].view(torch.int32).clone()
+    lead_gemm = ws.buf[n * 4: n * 8].view(torch.float32).clone()
+    stats_gemm = ws.buf[n * 8: n * 8 + 12 * B].view(torch.int32).clone()
     part = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
     got = zb.ops.decode_score(lo, (H, W), gt=gt, hist_partial=part, workspace=ws)                      # READY path
     ws2 = zb.ops.DecodeWorkspace()
     part2 = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
     got2 = zb.ops.decode_score(lo, (H, W), gt=gt, hist_partial=part2, workspace=ws2)                   # own pre-pass
     champ_own = ws2.buf[: n * 4].view(torch.int32)
-    stats_own = ws2.buf[n * 4: n * 4 + 12 * B].view(torch.int32)
+    lead_own = ws2.buf[n * 4: n * 8].view(torch.float32)
+    stats_own = ws2.buf[n * 8: n * 8 + 12 * B].view(torch.int32)
     finite = (stats_own[B:2 * B] == 0).repeat_interleave(h * w)
     assert torch.equal(champ_gemm[finite], champ_own[finite])
+    assert torch.equal(lead_gemm[finite], lead_own[finite])
+    flat = lo.permute(0, 2, 3, 1).reshape(n, Q)                      # lead = champion - best of the categories in front of it
+    before = torch.where(torch.arange(Q, device="cuda")[None, :] < champ_own[:, None].long(), flat, torch.full_like(flat, float("-inf"))).amax(dim=1)
+    want_lead = flat.gather(1, champ_own[:, None].long())[:, 0] - before
+    assert torch.equal(lead_own[finite], want_lead[finite])
     assert torch.equal(stats_gemm[B:2 * B] != 0, stats_own[B:2 * B] != 0) and stats_own[B:2 * B].tolist() == [0, 0, 0, 0, 1]
     assert torch.equal(stats_gemm[2 * B:3 * B - 1], stats_own[2 * B:3 * B - 1])                      # bits of max |logit| per finite image
     assert torch.equal(stats_own[2 * B:3 * B - 1].view(torch.float32), lo[:4].abs().amax(dim=(1, 2, 3)))

@@ -50,6 +50,8 @@ struct DecodeParams {
     int agree_min;           // an image is pruned when it is finite and >= agree_min neighbouring low-res pixels share their champion
     int* img_stats;          // [B] neighbour agreements | [B] non-finite flags | [B] bits of max |logit| (champion_kernel) | work counter
     const int* champ;        // [B*h*w] first-max category per low-res pixel
+    const float* lead;       // [B*h*w] its value minus the largest value of a category with a smaller index
+    long lead_delta;         // lead - champ in 4-byte elements
     int cap;                 // candidate slots per warp in the pruned kernel
     // byte offsets of the pruned kernel's tables in dynamic shared memory (computed by the host so that the kernel can
     // re-derive a pointer with one add instead of a chain of size computations when registers run out)
@@ -562,11 +564,12 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const
 constexpr int kPrunedWarps = 8;
 constexpr int kCellRun = 4;
 
-// Per low-res pixel: first-max category; per image: the number of horizontally adjacent pixels that share their
-// champion, a non-finite flag and max |logit|.  One block per (image, low-res row); 8 lanes per pixel read the pixel's
+// Per low-res pixel: first-max category and its lead over the categories in front of it; per image: the number of
+// horizontally adjacent pixels that share their champion, a non-finite flag and max |logit|.  One block per (image, low-res row); 8 lanes per pixel read the pixel's
 // categories as float4 (category index contiguous, 16-byte aligned pixels), 4 pixels per warp at a time.
 __global__ void __launch_bounds__(256) champion_kernel(const float* __restrict__ logits, long sb, long sy, long sx, int B, int Q,
-                                                       int h, int w, int* __restrict__ champ, int* __restrict__ stats) {
+                                                       int h, int w, int* __restrict__ champ, float* __restrict__ lead,
+                                                       int* __restrict__ stats) {
     extern __shared__ int s_row[];                            // [w]
     __shared__ int s_agree[8];
     const int b = blockIdx.x / h, y = blockIdx.x % h;
@@ -605,8 +608,23 @@ __global__ void __launch_bounds__(256) champion_kernel(const float* __restrict__
             if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
         }
         row_amax = fmaxf(row_amax, amax);
+        // second sweep (L1 hits): the best of the categories in front of the champion
+        float prev = -INFINITY;
+        if (x < w) {
+            const float4* v = reinterpret_cast<const float4*>(row + (long)x * sx);
+            for (int c = sub; c < chunks; c += 8) {
+                const float4 f = __ldg(v + c);
+                const float e[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (c * 4 + j < idx) prev = fmaxf(prev, e[j]);
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) prev = fmaxf(prev, __shfl_xor_sync(0xffffffffu, prev, o));
         if (sub == 0 && x < w) {
             champ[((long)b * h + y) * w + x] = idx;
+            lead[((long)b * h + y) * w + x] = __fsub_rn(best, prev);
             s_row[x] = idx;
         }
     }
@@ -687,6 +705,7 @@ __global__ void __launch_bounds__(kPrunedWarps * 32, 3) decode_pruned_kernel(con
         const float* row1 = p.logits + (long)b * p.sb + cy1 * sy;     //                    lower corners
         const int* ch0 = p.champ + ((size_t)b * p.h + cy) * p.w;
         const int* ch1 = p.champ + ((size_t)b * p.h + cy1) * p.w;
+
         // 2^-20 * max|logit of the image|, never 0: a champion must not dominate itself (its differences are exactly 0)
         const float margin = fmaxf(__int_as_float(p.img_stats[2 * p.B + b]) * 9.5367431640625e-07f, 1e-37f);
         // per-lane bases: lane = (row lane/8 [+4], column lane%8) of an 8x8 pixel tile; category lane (+32, +64, ..) of a tap
@@ -696,6 +715,14 @@ __global__ void __launch_bounds__(kPrunedWarps * 32, 3) decode_pruned_kernel(con
         const float* row0_lane = row0 + lane;
         const float* row1_lane = row1 + lane;
         const int W4 = 4 * p.W;
+        if (hist) {
+            // pull the run's ground truth towards L2 now (the whole-cell shortcut has nothing to hide its latency behind):
+            // lane = (row, 128-byte segment) of the run's pixel rectangle
+            const int xs_run = s_xstart[cx_begin], span = (s_xstart[cx_end] - xs_run) * (int)sizeof(GT);
+            const int segs = (span + 127) >> 7, r = lane / max(segs, 1), sgm = lane - r * max(segs, 1);
+            if (segs > 0 && ys + r < ye && r < 32)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(gt_base + (size_t)b * p.gt_sb + (size_t)(ys + r) * p.W + xs_run) + sgm * 128));
+        }
 
         // champions of the current cell's four corners; the next cell's right corners are requested one cell ahead
         int hA = __ldg(ch0 + cx_begin), hC = __ldg(ch1 + cx_begin);
@@ -710,6 +737,35 @@ __global__ void __launch_bounds__(kPrunedWarps * 32, 3) decode_pruned_kernel(con
             const float* pD = row1 + cx1 * sx;
             const int cx2 = min(cx + 2, p.w - 1);
             const int hBn = __ldg(ch0 + cx2), hDn = __ldg(ch1 + cx2);
+            // One champion at all four corners that leads every category in front of it by the margin at each of them wins
+            // the whole cell (the categories behind it can at best tie, and ties go to the smaller index): no taps, no
+            // survivor list, no evaluation.  Real segmentation maps are mostly such cells.
+            if (hA == hB && hA == hC && hA == hD) {
+                // the leads live lead_delta elements behind the champions (one constant instead of two more row pointers)
+                const float* ld0 = reinterpret_cast<const float*>(ch0) + p.lead_delta;
+                const float* ld1 = reinterpret_cast<const float*>(ch1) + p.lead_delta;
+                const float l = fminf(fminf(__ldg(ld0 + cx), __ldg(ld0 + cx1)), fminf(__ldg(ld1 + cx), __ldg(ld1 + cx1)));
+                if (l >= margin) {
+                    for (int ty = ys; ty < ye; ty += 8) {
+                        for (int tx = xs; tx < xe; tx += 8) {
+                            const bool okx = tx + (lane & 7) < xe, ok0 = okx && ty + (lane >> 3) < ye, ok1 = okx && ty + (lane >> 3) + 4 < ye;
+                            const int tile_off = (ty - ys) * p.W + tx;
+                            if (lbl_lane) {
+                                if (ok0) lbl_lane[tile_off] = (int16_t)hA;
+                                if (ok1) lbl_lane[tile_off + W4] = (int16_t)hA;
+                            }
+                            if (hist) {
+                                const int c0 = ok0 ? class_of<GT>(gt_lane[tile_off], p.n) : -1;
+                                const int c1 = ok1 ? class_of<GT>(gt_lane[tile_off + W4], p.n) : -1;
+                                warp_hist_add(hist, c0 >= 0 ? c0 * p.n + hA : -1);
+                                warp_hist_add(hist, c1 >= 0 ? c1 * p.n + hA : -1);
+                            }
+                        }
+                    }
+                    hA = hB; hC = hD; hB = hBn; hD = hDn;
+                    continue;
+                }
+            }
             // the four corner taps of this lane's categories (the left pair was the previous cell's right pair: L1 hits)
             float la_[NQ > 0 ? NQ : 1], lc_[NQ > 0 ? NQ : 1], rb_[NQ > 0 ? NQ : 1], rd_[NQ > 0 ? NQ : 1];
             if (NQ > 0) {
@@ -734,6 +790,7 @@ __global__ void __launch_bounds__(kPrunedWarps * 32, 3) decode_pruned_kernel(con
                 const int kk[4] = {hA, hB, hC, hD};
                 const bool use[4] = {true, kk[1] != kk[0], kk[2] != kk[0] && kk[2] != kk[1], kk[3] != kk[0] && kk[3] != kk[1] && kk[3] != kk[2]};
 
+                int n = 0;
                 // the champions' values at the four corners: lane 4c+r fetches corner r of champion c
                 __syncwarp();
                 if (lane < 16) {
@@ -746,7 +803,6 @@ __global__ void __launch_bounds__(kPrunedWarps * 32, 3) decode_pruned_kernel(con
                 const unsigned long long MINUS1 = pack2(-1.0f, -1.0f);
 
                 // survivors, ascending category order
-                int n = 0;
                 const int iters = NQ > 0 ? NQ : (p.Q + 31) >> 5;
 #pragma unroll
                 for (int it = 0; it < iters; ++it) {
@@ -1122,7 +1178,7 @@ static int decode_score_impl(const float* logits, long sb, long sq, long sy, lon
     p.labels = labels; p.hist = hist_partial; p.n = hist_partial ? n_classes : 1;
     p.identity = (H == h && W == w);
     p.XB = (W + 31) / 32; p.XR = 0; p.QC = 0; p.QS = 0; p.hist_in_smem = 0; p.n_items = 0; p.n_groups = 0; p.vec_stage = 0; p.gt_bytes = gt ? gt_dtype_bytes(gt_dtype) : 0;
-    p.select = 0; p.agree_min = 0; p.img_stats = nullptr; p.champ = nullptr; p.cap = 0;
+    p.select = 0; p.agree_min = 0; p.img_stats = nullptr; p.champ = nullptr; p.lead = nullptr; p.lead_delta = 0; p.cap = 0;
     p.off_ystart = p.off_xstart = p.off_ly = p.off_lx = p.off_img = p.off_warp = 0;
 
     const int sms = sm_count();
@@ -1204,14 +1260,15 @@ static int decode_score_impl(const float* logits, long sb, long sq, long sy, lon
             }
             if (psmem) {
                 int* champ = decode_ws_champ(workspace);
+                float* lead = decode_ws_lead(workspace, B, (long)h * w);
                 int* stats = decode_ws_stats(workspace, B, (long)h * w);
                 if (!champions_ready) {
                     ZUTIS_CUDA(cudaMemsetAsync(stats, 0, decode_ws_counter_bytes(B), stream));
-                    champion_kernel<<<(unsigned)(B * h), 256, (size_t)w * 4, stream>>>(logits, sb, sy, sx, B, Q, h, w, champ, stats);
+                    champion_kernel<<<(unsigned)(B * h), 256, (size_t)w * 4, stream>>>(logits, sb, sy, sx, B, Q, h, w, champ, lead, stats);
                     st = check_launch("champion_kernel");
                     if (st != ZUTIS_OK) return st;
                 }
-                p.champ = champ; p.img_stats = stats;
+                p.champ = champ; p.lead = lead; p.lead_delta = lead - reinterpret_cast<const float*>(champ); p.img_stats = stats;
                 // AUTO: an image is worth pruning when >= 10 % of its horizontally adjacent low-res pixels share their champion
                 // (model outputs: ~30 %; i.i.d. noise: 1 %); PRUNED forces every finite image through the pruned kernel
                 p.agree_min = mode == ZUTIS_DECODE_PRUNED ? 0 : (int)(((long)h * (w - 1) + 9) / 10);

@@ -12,7 +12,7 @@ struct GemmParams {
     int M; long N; int K; int sigmoid;
     // optional by-product for the pruned decode kernel (zutis_gemm_logits_champions): per pixel the first-max category,
     // per image the champion agreements of horizontally adjacent pixels, a non-finite flag and max |logit|
-    int* champ; int* img_stats; int img_w;
+    int* champ; float* lead; int* img_stats; int img_w;
 };
 
 #ifdef __CUDACC__

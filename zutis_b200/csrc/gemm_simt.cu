@@ -122,10 +122,11 @@ static int gemm_logits_impl(const float* A, long lda, long strideA,
     g.A = A; g.lda = lda; g.strideA = strideA; g.Bm = Bm; g.ldb = ldb; g.strideB = strideB;
     g.C = C; g.stride_cn = stride_cn; g.stride_cp = stride_cp; g.strideC = strideC;
     g.M = M; g.N = N; g.K = K; g.sigmoid = (flags & ZUTIS_GEMM_SIGMOID) ? 1 : 0;
-    g.champ = nullptr; g.img_stats = nullptr; g.img_w = 0;
+    g.champ = nullptr; g.lead = nullptr; g.img_stats = nullptr; g.img_w = 0;
     if (decode_workspace && img_w > 0 && N % img_w == 0 && decode_workspace_bytes >= decode_ws_bytes(batch, N) &&
         (reinterpret_cast<uintptr_t>(decode_workspace) & 7) == 0) {
-        g.champ = decode_ws_champ(decode_workspace); g.img_stats = decode_ws_stats(decode_workspace, batch, N); g.img_w = img_w;
+        g.champ = decode_ws_champ(decode_workspace); g.lead = decode_ws_lead(decode_workspace, batch, N);
+        g.img_stats = decode_ws_stats(decode_workspace, batch, N); g.img_w = img_w;
     }
     if (prec == ZUTIS_GEMM_FP32_SIMT) return launch_gemm_simt(g, batch, stream);
     if (!gemm_tcgen05_supports(g, batch, flags))

@@ -70,6 +70,7 @@ struct TcParams {
     int passes;       // 3 = hi*hi + hi*lo + lo*hi, 1 = hi*hi only
     int sigmoid;
     int* champ;       // optional: first-max category per pixel, for the pruned decode kernel
+    float* lead;      //           its value minus the largest value of a category with a smaller index
     int* img_stats;   // optional: [batch] adjacent-champion agreements | [batch] non-finite flags | [batch] bits of max |logit|
     int img_w;        // low-res image width (pixels per row), for the agreement count
 };
@@ -369,7 +370,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
             float* crow = p.C + (long)b * p.strideC + pix * p.stride_cp;
             const bool vec_ok = (p.stride_cn == 1) && ((p.stride_cp & 3) == 0) && ((p.strideC & 3) == 0) &&
                                 ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-            float ch_best = -INFINITY, ch_amax = 0.f;       // this pixel's champion (p.champ != nullptr: single category tile)
+            float ch_best = -INFINITY, ch_prev = -INFINITY, ch_amax = 0.f;   // this pixel's champion (p.champ != nullptr: single category tile)
             int ch_idx = 0x7fffffff;
             bool ch_bad = false;
             for (int c = 0; c < p.umma_n / 16; ++c) {
@@ -391,7 +392,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
                                 const float af = fabsf(f[j]);
                                 ch_bad = ch_bad || !(af <= 3.402823466e38f);
                                 ch_amax = fmaxf(ch_amax, af);
-                                if (f[j] > ch_best || ch_idx == 0x7fffffff) { ch_best = f[j]; ch_idx = n0 + j; }
+                                if (f[j] > ch_best || ch_idx == 0x7fffffff) {
+                                    ch_prev = ch_idx == 0x7fffffff ? -INFINITY : ch_best;       // the best of the categories before it
+                                    ch_best = f[j]; ch_idx = n0 + j;
+                                }
                             }
                         }
                     }
@@ -417,7 +421,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tmem_empty(a));
             if (p.champ) {
-                if (row_ok) p.champ[(long)b * p.N + pix] = ch_idx;
+                if (row_ok) { p.champ[(long)b * p.N + pix] = ch_idx; p.lead[(long)b * p.N + pix] = __fsub_rn(ch_best, ch_prev); }
                 // neighbours inside the warp only (1 pair in 32 is not counted: the count feeds a coarse threshold)
                 const int right = __shfl_down_sync(0xffffffffu, ch_idx, 1);
                 const bool pair = row_ok && lane < 31 && pix + 1 < p.N && ((pix + 1) % p.img_w) != 0 && right == ch_idx;
@@ -565,7 +569,7 @@ size_t gemm_tcgen05_workspace_bytes(int M, long, int K, int batch, int) {
 }
 
 bool gemm_tcgen05_makes_champions(const GemmParams& g) {
-    return g.champ && g.img_stats && g.img_w > 0 && make_plan(g.M).n_tiles == 1 && !g.sigmoid;
+    return g.champ && g.lead && g.img_stats && g.img_w > 0 && make_plan(g.M).n_tiles == 1 && !g.sigmoid;
 }
 
 bool gemm_tcgen05_supports(const GemmParams& g, int batch, int flags) {
@@ -618,8 +622,8 @@ int launch_gemm_tcgen05(const GemmParams& g, int batch, int flags, void* workspa
     p.passes = ((flags & ZUTIS_GEMM_PRECISION_MASK) == ZUTIS_GEMM_TF32X3) ? 3 : 1;
     p.sigmoid = g.sigmoid;
     // the champion by-product needs every category of a pixel in one thread: single category tile, raw logits
-    const bool champs = g.champ && g.img_stats && g.img_w > 0 && pl.n_tiles == 1 && !g.sigmoid;
-    p.champ = champs ? g.champ : nullptr; p.img_stats = champs ? g.img_stats : nullptr; p.img_w = g.img_w;
+    const bool champs = g.champ && g.lead && g.img_stats && g.img_w > 0 && pl.n_tiles == 1 && !g.sigmoid;
+    p.champ = champs ? g.champ : nullptr; p.lead = champs ? g.lead : nullptr; p.img_stats = champs ? g.img_stats : nullptr; p.img_w = g.img_w;
 
     if (champs) ZUTIS_CUDA(cudaMemsetAsync(g.img_stats, 0, decode_ws_counter_bytes(batch), stream));
     const size_t smem = pl.smem;

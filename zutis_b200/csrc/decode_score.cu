@@ -548,9 +548,10 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const
 // A_k >= A_j, B_k >= B_j, C_k >= C_j and D_k >= D_j then v_k >= v_j at EVERY pixel of the cell, in floating point.
 // Category j can therefore never be the first maximum anywhere in the cell when some k dominates it that way and
 //   * k < j (a tie still goes to k), or
-//   * k > j and the dominance holds with a margin m = 2^-20 * max|logit of the image|: the exact difference is
-//     then >= m * (1 - 2^-22) while three roundings per interpolant move the two values by at most 6 * 2^-24 * max|.|
-//     together, so v_k > v_j strictly.
+//   * k > j and the dominance holds with a margin m = 2^-20 * M, M = max|logit of the image|: the exact difference
+//     of the two interpolants is then >= m * (1 - 2^-22) (the weights sum to >= 1 - 2^-23, the margin test itself
+//     rounds once), while the roundings of one interpolant (two products and three fmas, each relative 2^-24 on terms
+//     whose weighted magnitudes sum to <= 4 M) move it by <= 2^-22 M, the pair by <= 2^-21 M < m: v_k > v_j strictly.
 // Only the four corner champions (first maxima of the corner pixels, found once per low-res pixel by champion_kernel)
 // are tried as dominators.  On model-like logits 6 of 81 categories survive per cell (22 of 920); the survivors'
 // corner values are compacted into shared memory and the warp (lane = pixel of an 8x8 tile, 2 pixels per lane) walks

@@ -204,7 +204,7 @@ def _smooth_logits(B, Q, h, w, gen, contrast=1.0):
     return (contrast * torch.nn.functional.interpolate(coarse, size=(h, w), mode="bilinear", align_corners=True)).contiguous()
 
 
-@pytest.mark.parametrize("case", ["smooth", "smooth_noninteger", "x16", "x6", "iid", "ties", "nonfinite_mix", "wide", "wide_overflow", "hist_only", "uniform_regions"])
+@pytest.mark.parametrize("case", ["smooth", "smooth_noninteger", "x16", "x6", "iid", "ties", "nonfinite_mix", "wide", "wide_overflow", "hist_only", "uniform_regions", "near_ties"])
 def test_pruned_kernel_is_exact(zb, case):
     """The candidate-pruning kernel must give the generic kernel's labels and histogram bit for bit -- on coherent
     logits (where it prunes), on noise (where nearly everything survives), on exact ties and duplicated categories
@@ -239,6 +239,14 @@ def test_pruned_kernel_is_exact(zb, case):
         lo.scatter_add_(1, region[:, None], torch.ones(B, 1, h, w))
         lo[1, 3] = lo[1, 7]                                               # a duplicated category inside the uniform regions
         lo[2, :, :8] = 0.25                                               # a region where every category ties exactly: label 0
+    elif case == "near_ties":                                             # differences right at the scale of the pruning margin
+        B, Q, h, w, H, W = 4, 32, 12, 12, 96, 96
+        base = _smooth_logits(B, 8, h, w, gen)
+        lo = base.repeat(1, 4, 1, 1)                                      # every category has three exact copies ...
+        scale = lo.abs().amax() * torch.tensor([2.0 ** -e for e in (24, 23, 22, 21, 20, 19, 18)])
+        pick = torch.randint(0, 7, lo.shape, generator=gen)
+        sign = torch.randint(0, 3, lo.shape, generator=gen).float() - 1.0  # ... perturbed by 0 or +-2^-24..2^-18 of the maximum
+        lo = (lo + sign * scale[pick]).contiguous()
     elif case == "wide":
         B, Q, h, w, H, W = 1, 920, 7, 8, 56, 64; lo = _smooth_logits(B, Q, h, w, gen, 0.2)
     elif case == "wide_overflow":                                         # noise: ~390 of 600 categories survive, more than the 256 slots

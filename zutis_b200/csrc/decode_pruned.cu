@@ -21,10 +21,13 @@ namespace zutis {
 // are tried as dominators.  On model-like logits 6 of 81 categories survive per cell (22 of 920); the survivors'
 // corner values are compacted into shared memory and the warp (lane = pixel of an 8x8 tile, 2 pixels per lane) walks
 // only those, in ascending category order with a strict compare = torch.argmax's first maximum.
-// A warp walks a run of kCellRun horizontally adjacent cells (runs are handed out through an atomic counter): the right corners (B, D) of one cell are the left
-// corners (A, C) of the next and stay in registers (NQ = ceil(Q/32) values per lane and corner, NQ = 0: wide Q, taps
-// re-read per cell).  The ground truth of a cell's first tile is requested before the pruning work so that its
-// latency is hidden.
+// A cell whose four corners share one champion that leads every category in front of it by the margin is labelled
+// without reading a tap (the categories behind the champion can at best tie): most cells of a real segmentation map.
+// A warp walks a run of kCellRun horizontally adjacent cells (runs are handed out through an atomic counter); the next
+// cell's champions are requested one cell ahead, the corner taps (NQ = ceil(Q/32) values per lane and corner; NQ = 0:
+// wide Q, read inside the loop) are re-read per cell -- the left pair hits L1 -- because carrying them in registers
+// cost more than the loads.  The ground truth of a run is pulled towards L2 at its start and the first tile's labels
+// are requested before the pruning work, so that their latency is hidden.
 // Images with a non-finite logit (NaN ordering) or without spatial coherence (pruning would not pay) are left to the
 // tiled kernel; both kernels derive the same image split from champion_kernel's per-image counters.
 constexpr int kPrunedWarps = 8;

@@ -148,12 +148,14 @@ def predict(
     text = self.text_embeddings
     if mask_type == "semantic":
         tokens = dict_outputs["patch_tokens"]                      # b x h x w x n_dims
+        ws = self.__dict__.setdefault("_zutis_b200_decode_ws", ops.DecodeWorkspace())   # champions for the pruning decode kernel
         lowres = ops.contraction(text.to(tokens.device), tokens, precision=precision,
-                                 a_cache=self.__dict__.setdefault("_zutis_b200_text_cache", {}))       # b x n x h x w
+                                 a_cache=self.__dict__.setdefault("_zutis_b200_text_cache", {}),
+                                 decode_ws=None if return_logits else ws)                              # b x n x h x w
         if return_logits:
             # the one mode in which full-resolution logits are materialised, on request (zutis.py:369-370)
             return ops.upsample_bilinear(lowres, size) if size is not None else lowres
-        labels = ops.decode_score(lowres, size)                    # int16 on the device
+        labels = ops.decode_score(lowres, size, workspace=ws)      # int16 on the device
         return labels.cpu().numpy().astype(np.int64)
 
     mask_proposals: torch.Tensor = dict_outputs["mask_proposals"]

@@ -102,6 +102,28 @@ __device__ __forceinline__ void build_image_list(const DecodeParams& p, int want
     }
 }
 
+// Add a CTA's shared-memory histogram into the global int32 partial.  Two neighbouring bins travel in ONE 64-bit atomic
+// when the partial is 8-byte aligned: counts are non-negative and the whole partial stays below 2^31 (the entry point
+// checks B*H*W), so the low word never carries into the high one.  All CTAs flush at about the same time, which makes
+// this a burst of (#CTAs x non-zero bins) L2 atomics; halving it is measurable.
+__device__ __forceinline__ void flush_shared_hist(const int* s_hist, int* hist, int nn) {
+    if ((reinterpret_cast<uintptr_t>(hist) & 7) == 0) {
+        const int pairs = nn >> 1;
+        for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
+            const int2 v = reinterpret_cast<const int2*>(s_hist)[i];
+            if (v.x | v.y)
+                atomicAdd(reinterpret_cast<unsigned long long*>(hist) + i,
+                          (unsigned long long)(unsigned)v.x | ((unsigned long long)(unsigned)v.y << 32));
+        }
+        if ((nn & 1) && threadIdx.x == 0 && s_hist[nn - 1]) atomicAdd(hist + nn - 1, s_hist[nn - 1]);
+    } else {
+        for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+            const int v = s_hist[i];
+            if (v) atomicAdd(hist + i, v);
+        }
+    }
+}
+
 // decode_pruned.cu.  Sets up and launches the pruned kernel (and the champion pass unless the workspace already
 // holds the champions of these logits) for the images it owns; on success *launched = true and p.select = 1, so that
 // the tiled kernel launched next takes the remaining images.  forced = ZUTIS_DECODE_PRUNED (every finite image).

@@ -441,10 +441,7 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const
     cp_async_wait_all();
     if (p.hist && p.hist_in_smem) {
         __syncthreads();
-        for (int i = threadIdx.x; i < nn; i += blockDim.x) {
-            const int v = s_hist[i];
-            if (v) atomicAdd(p.hist + i, v);
-        }
+        flush_shared_hist(s_hist, p.hist, nn);
     }
 }
 

@@ -370,9 +370,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
             float* crow = p.C + (long)b * p.strideC + pix * p.stride_cp;
             const bool vec_ok = (p.stride_cn == 1) && ((p.stride_cp & 3) == 0) && ((p.strideC & 3) == 0) &&
                                 ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-            float ch_best = -INFINITY, ch_prev = -INFINITY, ch_amax = 0.f;   // this pixel's champion (p.champ != nullptr: single category tile)
-            int ch_idx = 0x7fffffff;
-            bool ch_bad = false;
+            // this pixel's champion (p.champ != nullptr: single category tile).  A finite first category always replaces
+            // -inf, so no "unset" state is needed; in an image with a non-finite logit the champions are never used.
+            float ch_best = -INFINITY, ch_prev = -INFINITY;
+            int ch_idx = 0;
+            unsigned ch_abs = 0;                               // max of the magnitude bits: NaN and inf are >= 0x7f800000
             for (int c = 0; c < p.umma_n / 16; ++c) {
                 uint32_t v[16];
                 tmem_ld_x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * p.umma_n + c * 16), v);
@@ -386,16 +388,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
                         if (p.sigmoid) f[j] = sigmoidf_exact(f[j]);
                     }
                     if (p.champ) {
+                        const bool whole = n0 + 16 <= p.M;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            if (n0 + j < p.M) {
-                                const float af = fabsf(f[j]);
-                                ch_bad = ch_bad || !(af <= 3.402823466e38f);
-                                ch_amax = fmaxf(ch_amax, af);
-                                if (f[j] > ch_best || ch_idx == 0x7fffffff) {
-                                    ch_prev = ch_idx == 0x7fffffff ? -INFINITY : ch_best;       // the best of the categories before it
-                                    ch_best = f[j]; ch_idx = n0 + j;
-                                }
+                            if (whole || n0 + j < p.M) {
+                                ch_abs = max(ch_abs, __float_as_uint(f[j]) & 0x7fffffffu);
+                                if (f[j] > ch_best) { ch_prev = ch_best; ch_best = f[j]; ch_idx = n0 + j; }   // prev: best of the categories before it
                             }
                         }
                     }
@@ -426,8 +424,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
                 const int right = __shfl_down_sync(0xffffffffu, ch_idx, 1);
                 const bool pair = row_ok && lane < 31 && pix + 1 < p.N && ((pix + 1) % p.img_w) != 0 && right == ch_idx;
                 const int agree = __popc(__ballot_sync(0xffffffffu, pair));
-                const bool bad = __any_sync(0xffffffffu, ch_bad && row_ok);
-                int amax_bits = row_ok ? __float_as_int(ch_amax) : 0;
+                const bool bad = __any_sync(0xffffffffu, ch_abs >= 0x7f800000u && row_ok);
+                int amax_bits = row_ok ? (int)ch_abs : 0;
                 for (int o = 16; o > 0; o >>= 1) amax_bits = max(amax_bits, __shfl_xor_sync(0xffffffffu, amax_bits, o));
                 if (lane == 0) {
                     if (agree) atomicAdd(p.img_stats + b, agree);

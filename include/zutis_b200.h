@@ -98,8 +98,9 @@ ZUTIS_API int zutis_gemm_logits(const float* A, long lda, long strideA,
                                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* The same contraction, which additionally leaves in `decode_workspace` (>= zutis_decode_workspace_bytes) what the
- * candidate-pruning decode kernel needs per low-res pixel (first-max category, max |logit|) and per image (champion
- * agreement of adjacent pixels, non-finite flag), computed in the epilogue while the logits are still in registers.
+ * candidate-pruning decode kernel needs per low-res pixel (first-max category = the low-res argmax, and its lead over
+ * the categories with a smaller index) and per image (champion agreement of adjacent pixels, non-finite flag,
+ * max |logit|), computed in the epilogue while the logits are still in registers.
  * img_w = low-res image width (N % img_w == 0).  *champions_written (host int, may be NULL) is set to 1 when the
  * by-product was produced (tensor-core path, <= 256 categories, no sigmoid); pass ZUTIS_DECODE_CHAMPIONS_READY in the
  * decode mode only in that case -- otherwise zutis_decode_score_ws computes the same data itself. */
@@ -134,11 +135,12 @@ ZUTIS_API int zutis_decode_score(const float* logits, long sb, long sq, long sy,
 
 /* Same contract with a caller-provided device workspace (>= zutis_decode_workspace_bytes, 8-byte aligned), which
  * enables the exact candidate-pruning kernel: per low-res cell only the categories that no corner champion dominates
- * at all four corner taps are interpolated (monotonicity of the bilinear expression, csrc/decode_score.cu).  Results
+ * at all four corner taps are interpolated (monotonicity of the bilinear expression, csrc/decode_pruned.cu).  Results
  * are identical to zutis_decode_score; ZUTIS_DECODE_AUTO sends each finite, spatially coherent image through the
  * pruned kernel and the others through the tiled kernel, ZUTIS_DECODE_PRUNED forces every finite image through it
- * (needs category index contiguous, sq == 1, and >= 4x up-sampling).  workspace == NULL behaves like
- * zutis_decode_score. */
+ * (needs category index contiguous, sq == 1, 16-byte aligned pixels, >= 4x up-sampling and B <= 1024).  workspace ==
+ * NULL behaves like zutis_decode_score.  The workspace is scratch: its content is consumed by the call (a
+ * ZUTIS_DECODE_CHAMPIONS_READY workspace serves the decode of exactly the logits it was filled for). */
 ZUTIS_API size_t zutis_decode_workspace_bytes(int B, int Q, int h, int w, int H, int W);
 ZUTIS_API int zutis_decode_score_ws(const float* logits, long sb, long sq, long sy, long sx,
                                     int B, int Q, int h, int w, int H, int W,

@@ -297,7 +297,7 @@ def test_contraction_epilogue_champions_equal_decode_prepass(zb):
     gt = torch.randint(0, Q, (B, H, W), generator=gen).cuda()
     ws = zb.ops.DecodeWorkspace()
     lo = zb.ops.contraction(text, tokens, precision="tf32x3", decode_ws=ws)
-    assert ws.ready_for == (lo.data_ptr(), (B, Q, h, w))
+    assert ws.ready_for == (lo.data_ptr(), (B, Q, h, w), lo._version)
     n = B * h * w                                                   # workspace: champions [n] int32 | leads [n] fp32 | counters [3*B] int32
     assert n % 2 == 0
     champ_gemm = ws.buf[: n * 4].view(torch.int32).clone()
@@ -326,6 +326,12 @@ def test_contraction_epilogue_champions_equal_decode_prepass(zb):
     ref_part = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
     ref = zb.ops.decode_score(lo, (H, W), gt=gt, hist_partial=ref_part, mode=_ffi.DECODE_GENERIC)
     assert torch.equal(got, ref) and torch.equal(got2, ref) and torch.equal(part, ref_part) and torch.equal(part2, ref_part)
+    # logits changed in place after the contraction: the stale champions must not be trusted
+    ws3 = zb.ops.DecodeWorkspace()
+    lo3 = zb.ops.contraction(text, tokens, precision="tf32x3", decode_ws=ws3)
+    lo3[:, 5] += 1.0
+    want3 = zb.ops.decode_score(lo3, (H, W), mode=_ffi.DECODE_GENERIC)
+    assert torch.equal(zb.ops.decode_score(lo3, (H, W), workspace=ws3), want3)
     meter = zb.RunningScore(Q)
     labels = zb.decode_and_score(text, tokens, gt, (H, W), meter, want_labels=True, precision="tf32x3")
     assert torch.equal(labels, ref) and torch.equal(meter.counts().view(-1).to(torch.int32), ref_part)

@@ -59,7 +59,7 @@ class DecodeWorkspace:
 
     def __init__(self):
         self.buf: Optional[torch.Tensor] = None
-        self.ready_for: Optional[tuple] = None      # (logits data_ptr, shape) the champions in ``buf`` belong to
+        self.ready_for: Optional[tuple] = None      # (logits data_ptr, shape, version) the champions in ``buf`` belong to
 
     def ensure(self, nbytes: int, device) -> torch.Tensor:
         if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
@@ -135,7 +135,8 @@ def contraction(a: torch.Tensor, feats: torch.Tensor, *, precision: Optional[str
                        ws.data_ptr() if ws is not None else None, ws_bytes,
                        w, dws.data_ptr(), dws_bytes, C.addressof(written), _stream())
                 if written.value:
-                    decode_ws.ready_for = (buf.data_ptr(), (B, M, h, w))
+                    # (pointer, shape, autograd version): an in-place change of the logits invalidates the champions
+                    decode_ws.ready_for = (buf.data_ptr(), (B, M, h, w), buf._version)
             else:
                 F.call("zutis_gemm_logits", a.data_ptr(), a.stride(-2), 0 if shared else a.stride(0),
                        feats.data_ptr(), feats.stride(2), feats.stride(0),
@@ -189,7 +190,7 @@ def decode_score(logits: torch.Tensor, size=None, *, gt: Optional[torch.Tensor] 
         ws_bytes = F.lib().zutis_decode_workspace_bytes(B, Q, h, w, H, W)
         if workspace is not None:
             ws = workspace.ensure(ws_bytes, logits.device)
-            if workspace.ready_for == (logits.data_ptr(), (B, Q, h, w)):
+            if workspace.ready_for == (logits.data_ptr(), (B, Q, h, w), logits._version):
                 mode |= F.DECODE_CHAMPIONS_READY             # the contraction's epilogue already filled it for these logits
             workspace.ready_for = None
         else:

@@ -15,6 +15,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _native_library():
+    """Build libzutis_b200.so when a fresh checkout does not have it yet (nvcc cross-compiles without a GPU)."""
+    from zutis_b200 import _ffi
+    if not os.path.exists(_ffi.LIB_PATH):
+        import shutil
+        if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+            from zutis_b200 import build
+            build.build()
+    yield
+
+
 @pytest.fixture(scope="session")
 def golden():
     def load(name):

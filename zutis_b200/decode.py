@@ -3,10 +3,10 @@
 ``predict`` and ``get_mask_proposals`` keep the reference signatures and return types
 (networks/zutis.py:340-353 and :177-182) and are written to be bound onto the reference model::
 
-    from zutis_b200 import install; install(ZUTIS)      # ZUTIS.predict / get_mask_proposals now run on libzutis_b200
+    from zutis_b200 import install; install(ZUTIS)      # ZUTIS.predict now runs on libzutis_b200
 
-or used through ``ZutisDecoder`` (an object holding only ``text_embeddings``).  ``forward`` is
-untouched.  What changes is what runs underneath:
+or used through ``ZutisDecoder`` (an object holding only ``text_embeddings``).  ``forward`` and everything it
+calls are untouched by default, so training keeps its autograd graph (see ``install``).  What changes is what runs underneath:
 
   semantic (zutis.py:355-372)  einsum -> tcgen05 / FFMA contraction kernel (pixel-major logits);
                                F.interpolate + argmax -> one fused kernel that never writes the
@@ -284,8 +284,38 @@ class ZutisDecoder:
         return decode_and_score(self.text_embeddings, patch_tokens, label_trues, size, meter, want_labels, precision)
 
 
-def install(zutis_cls) -> None:
-    """Bind the B200 decode path onto the reference model class (``networks.zutis.ZUTIS``)."""
+def _wants_autograd(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+
+
+def install(zutis_cls, inference_forward_ops: bool = False) -> None:
+    """Bind the B200 decode path onto the reference model class (``networks.zutis.ZUTIS``).
+
+    By default only ``predict`` is replaced: it is the evaluation entry (``@torch.no_grad()`` in the reference,
+    zutis.py:340) and nothing in ``forward`` calls it, so ``trainer.fit`` trains exactly as before.
+    ``get_mask_proposals`` and ``image_to_text_space`` ARE called by ``forward`` (zutis.py:522-530), whose outputs feed
+    the training criterion; the kernels behind this module have no backward.  With ``inference_forward_ops=True``
+    they are bound as well, behind a guard: whenever autograd is recording and an input (or the projection) requires
+    grad, the call goes to the reference's own method, untouched; the kernels only serve no-grad forwards
+    (``trainer.evaluate``, ``coco20k_eval.py``)."""
     zutis_cls.predict = predict
-    zutis_cls.get_mask_proposals = get_mask_proposals
-    zutis_cls.image_to_text_space = image_to_text_space
+    if not inference_forward_ops:
+        return
+    ref_proposals = zutis_cls.get_mask_proposals
+    ref_text_space = zutis_cls.image_to_text_space
+
+    def guarded_get_mask_proposals(self, queries, patch_tokens, return_binary_masks: bool = True):
+        if _wants_autograd(queries, patch_tokens) or not patch_tokens.is_cuda:
+            return ref_proposals(self, queries, patch_tokens, return_binary_masks)
+        return get_mask_proposals(self, queries, patch_tokens, return_binary_masks)
+
+    def guarded_image_to_text_space(self, patch_tokens, proj, channel_last, layer_norm: bool = True):
+        if (_wants_autograd(patch_tokens, proj) or not patch_tokens.is_cuda or not channel_last
+                or "RN" in getattr(self, "clip_arch", "ViT")):
+            return ref_text_space(self, patch_tokens, proj, channel_last, layer_norm)
+        return image_to_text_space(self, patch_tokens, proj, channel_last, layer_norm)
+
+    guarded_get_mask_proposals.__wrapped__ = ref_proposals
+    guarded_image_to_text_space.__wrapped__ = ref_text_space
+    zutis_cls.get_mask_proposals = guarded_get_mask_proposals
+    zutis_cls.image_to_text_space = guarded_image_to_text_space

@@ -9,6 +9,7 @@ from __future__ import annotations
 from typing import Optional, Tuple
 
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
@@ -32,6 +33,15 @@ def _stream() -> int:
 def _need_cuda(t: torch.Tensor, name: str) -> None:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise TypeError(f"{name} must be a CUDA tensor (zutis_b200 has no CPU path)")
+
+
+def _fp32_4d(t: torch.Tensor, name: str) -> torch.Tensor:
+    """The kernels read raw fp32: half-precision inputs (autocast) are widened, anything else is refused."""
+    if t.dim() != 4:
+        raise ValueError(f"{name} must be 4-D, got {tuple(t.shape)}")
+    if not t.is_floating_point():
+        raise TypeError(f"{name} must be a floating-point tensor, got {t.dtype}")
+    return t if t.dtype == torch.float32 else t.float()
 
 
 def size_pair(size) -> Optional[Tuple[int, int]]:
@@ -59,13 +69,25 @@ class DecodeWorkspace:
 
     def __init__(self):
         self.buf: Optional[torch.Tensor] = None
-        self.ready_for: Optional[tuple] = None      # (logits data_ptr, shape, version) the champions in ``buf`` belong to
+        # (weakref to the logits buffer, shape, version) the champions in ``buf`` belong to.  A weak reference, not a
+        # data pointer: the caching allocator hands a freed address (with version 0) to the next tensor of that size.
+        self.ready_for: Optional[tuple] = None
 
     def ensure(self, nbytes: int, device) -> torch.Tensor:
         if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
             self.buf = torch.empty(max(nbytes, 8), device=device, dtype=torch.uint8)
             self.ready_for = None
         return self.buf
+
+    def mark_ready(self, logits_buf: torch.Tensor, shape: tuple) -> None:
+        self.ready_for = (weakref.ref(logits_buf), tuple(shape), logits_buf._version)
+
+    def holds_champions_of(self, logits: torch.Tensor) -> bool:
+        if self.ready_for is None:
+            return False
+        ref, shape, version = self.ready_for
+        base = logits._base if logits._base is not None else logits
+        return ref() is base and tuple(logits.shape) == shape and logits._version == version
 
 
 def contraction(a: torch.Tensor, feats: torch.Tensor, *, precision: Optional[str] = None, sigmoid: bool = False,
@@ -113,14 +135,19 @@ def contraction(a: torch.Tensor, feats: torch.Tensor, *, precision: Optional[str
     def launch(fl: int) -> None:
         ws_bytes = F.lib().zutis_gemm_workspace_bytes(M, N, Cc, 1 if shared else B, fl)
         ws = None
+        cache_key = None
         if ws_bytes and shared and a_cache is not None:
-            key = (a.data_ptr(), a._version, M, Cc, fl & F.GEMM_TF32X3 | fl & F.GEMM_TF32, str(feats.device))
-            ws = a_cache.get(key)
-            if ws is None:
-                a_cache.clear()
-                ws = a_cache[key] = torch.empty(ws_bytes, device=feats.device, dtype=torch.uint8)
-            else:
+            # The prepared operand belongs to THIS tensor object at THIS version.  The entry keeps a reference to the
+            # tensor and is compared with `is`: a data pointer would be recycled by the caching allocator when
+            # update_text_embeddings (zutis.py:333-338) replaces the embeddings by a tensor of the same size.
+            cache_key = (M, Cc, fl & F.GEMM_TF32X3 | fl & F.GEMM_TF32, str(feats.device))
+            hit = a_cache.get("entry")
+            if hit is not None and hit[0] is a and hit[1] == a._version and hit[2] == cache_key:
+                ws = hit[3]
                 fl |= F.GEMM_A_PREPARED
+            else:
+                a_cache.clear()
+                ws = torch.empty(ws_bytes, device=feats.device, dtype=torch.uint8)
         elif ws_bytes:
             ws = torch.empty(ws_bytes, device=feats.device, dtype=torch.uint8)
         with torch.cuda.device(feats.device):
@@ -135,13 +162,14 @@ def contraction(a: torch.Tensor, feats: torch.Tensor, *, precision: Optional[str
                        ws.data_ptr() if ws is not None else None, ws_bytes,
                        w, dws.data_ptr(), dws_bytes, C.addressof(written), _stream())
                 if written.value:
-                    # (pointer, shape, autograd version): an in-place change of the logits invalidates the champions
-                    decode_ws.ready_for = (buf.data_ptr(), (B, M, h, w), buf._version)
+                    decode_ws.mark_ready(buf, (B, M, h, w))      # an in-place change of the logits invalidates the champions
             else:
                 F.call("zutis_gemm_logits", a.data_ptr(), a.stride(-2), 0 if shared else a.stride(0),
                        feats.data_ptr(), feats.stride(2), feats.stride(0),
                        buf.data_ptr(), s_cn, s_cp, s_c, M, N, Cc, B, fl,
                        ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
+        if cache_key is not None and not (fl & F.GEMM_A_PREPARED):
+            a_cache["entry"] = (a, a._version, cache_key, ws)    # only once the launch that prepared it has succeeded
 
     if (precision or DEFAULT_PRECISION) == "auto":
         try:
@@ -190,7 +218,7 @@ def decode_score(logits: torch.Tensor, size=None, *, gt: Optional[torch.Tensor] 
         ws_bytes = F.lib().zutis_decode_workspace_bytes(B, Q, h, w, H, W)
         if workspace is not None:
             ws = workspace.ensure(ws_bytes, logits.device)
-            if workspace.ready_for == (logits.data_ptr(), (B, Q, h, w), logits._version):
+            if workspace.holds_champions_of(logits):
                 mode |= F.DECODE_CHAMPIONS_READY             # the contraction's epilogue already filled it for these logits
             workspace.ready_for = None
         else:
@@ -225,6 +253,7 @@ def hist_merge(partials: torch.Tensor, hist_i64: torch.Tensor, clear: bool = Tru
 def upsample_bilinear(x: torch.Tensor, size) -> torch.Tensor:
     """F.interpolate(x, size, mode="bilinear") materialised (return_logits=True, zutis.py:366-370)."""
     _need_cuda(x, "x")
+    x = _fp32_4d(x, "x")
     B, Q, h, w = x.shape
     H, W = size_pair(size)
     out = torch.empty((B, Q, H, W), device=x.device, dtype=torch.float32)
@@ -237,6 +266,7 @@ def upsample_bilinear(x: torch.Tensor, size) -> torch.Tensor:
 def decode_threshold(probs: torch.Tensor, size=None, threshold: float = 0.5, want_areas: bool = True):
     """interp(probs) > threshold as bit-packed masks uint32-in-int32 [B,Q,H,words] (+ int32 areas [B,Q])."""
     _need_cuda(probs, "probs")
+    probs = _fp32_4d(probs, "probs")
     B, Q, h, w = probs.shape
     hw = size_pair(size)
     H, W = hw if hw is not None else (h, w)
@@ -335,7 +365,7 @@ def mask_rle_strings(bits: torch.Tensor, W: int, mask_ids: Optional[torch.Tensor
     meta_h = meta.cpu().numpy()
     used = int(meta_h[0])
     if used > capacity:
-        raise F.ZutisError(f"zutis_rle_to_string needed {used} bytes, {capacity} were provided")
+        raise F.ZutisError(F.ERR_WORKSPACE, f"zutis_rle_to_string needed {used} bytes, {capacity} were provided")
     buf = strings[:used].cpu().numpy().tobytes()
     lens = lengths.cpu().numpy()
     return [buf[o:o + l] for o, l in zip(meta_h[1:].tolist(), lens.tolist())], boxes.cpu().numpy()
@@ -344,7 +374,12 @@ def mask_rle_strings(bits: torch.Tensor, W: int, mask_ids: Optional[torch.Tensor
 def instance_lowres_stats(probs: torch.Tensor, tokens: Optional[torch.Tensor], threshold: float = 0.5):
     """sizes int32 [B,Q], psum fp32 [B,Q], mean_tokens fp32 [B,Q,D]   (zutis.py:390-406)."""
     _need_cuda(probs, "probs")
+    probs = _fp32_4d(probs, "probs")
     B, Q, h, w = probs.shape
+    if tokens is not None:
+        _need_cuda(tokens, "tokens")
+        if tokens.dim() != 4 or tuple(tokens.shape[:3]) != (B, h, w):
+            raise ValueError(f"tokens must be [B,h,w,D] = [{B},{h},{w},D], got {tuple(tokens.shape)}")
     sizes = torch.empty((B, Q), device=probs.device, dtype=torch.int32)
     psum = torch.empty((B, Q), device=probs.device, dtype=torch.float32)
     mean = None

@@ -57,8 +57,8 @@ def parse_args():
                     help="tokens of a trained-model-like output: piecewise-constant label regions + noise (informational; "
                          "the default stays the random-init model-like field SURVEY 8d specifies)")
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x3", "tf32"])
-    ap.add_argument("--decode", default="auto", choices=["auto", "tiled", "pruned", "generic"],
-                    help="decode kernel: auto = exact candidate pruning on coherent images, tiled brute force otherwise")
+    ap.add_argument("--decode", default="auto", choices=["auto", "tiled", "cells", "generic"],
+                    help="decode kernel: auto = exact per-cell candidate pruning (cells) when the shape allows")
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -291,23 +291,18 @@ def run_ours(args, cfg, rank, local, world):
                                      Q, h * w, D, B, flags, ws.data_ptr(), ws_bytes, stream))
     step_flags = flags | (_ffi.GEMM_A_PREPARED if (flags & 3) != 0 else 0)
 
-    # scratch of the candidate-pruning decode kernel (champion per low-res pixel)
+    # the cell decode kernel's run counter: zero-filled once, left zero by every launch
     dws_bytes = _ffi.lib().zutis_decode_workspace_bytes(B, Q, h, w, H, W)
-    dws = torch.empty(max(dws_bytes, 8), dtype=torch.uint8, device=device)
-    decode_mode = {"auto": _ffi.DECODE_AUTO, "tiled": _ffi.DECODE_TILED, "pruned": _ffi.DECODE_PRUNED, "generic": _ffi.DECODE_GENERIC}[args.decode]
-
-    import ctypes
-    champs_written = ctypes.c_int(0)
+    dws = torch.zeros(max(dws_bytes, 16), dtype=torch.uint8, device=device)
+    decode_mode = {"auto": _ffi.DECODE_AUTO, "tiled": _ffi.DECODE_TILED, "cells": _ffi.DECODE_CELLS, "generic": _ffi.DECODE_GENERIC}[args.decode]
 
     def step(i, ev=None):
         _, tokens, gt = sets[i % n_sets]
         if ev: ev[0].record()
-        # the tensor-core contraction leaves the pruning kernel's per-pixel champions in `dws` (epilogue by-product)
-        _ffi.check(lib.zutis_gemm_logits_champions(text.data_ptr(), D, 0, tokens.data_ptr(), D, h * w * D, logits_buf.data_ptr(), 1, Qp, h * w * Qp,
-                                                   Q, h * w, D, B, step_flags, ws.data_ptr(), ws_bytes,
-                                                   w, dws.data_ptr(), dws_bytes, ctypes.addressof(champs_written), stream))
+        _ffi.check(lib.zutis_gemm_logits(text.data_ptr(), D, 0, tokens.data_ptr(), D, h * w * D, logits_buf.data_ptr(), 1, Qp, h * w * Qp,
+                                         Q, h * w, D, B, step_flags, ws.data_ptr(), ws_bytes, stream))
         if ev: ev[1].record()
-        mode = decode_mode | (_ffi.DECODE_CHAMPIONS_READY if champs_written.value else 0)
+        mode = decode_mode | _ffi.DECODE_WORKSPACE_ZEROED
         _ffi.check(lib.zutis_decode_score_ws(logits.data_ptr(), h * w * Qp, 1, w * Qp, Qp, B, Q, h, w, H, W, gt.data_ptr(), _ffi.GT_I64, H * W,
                                              labels.data_ptr(), meter._partial.data_ptr(), Q, mode, dws.data_ptr(), dws_bytes, stream))
         if ev: ev[2].record()
@@ -396,10 +391,9 @@ def run_ours(args, cfg, rank, local, world):
     bytes_decode = B * (4 * Q * h * w + 8 * H * W + 2 * H * W)
     bytes_gemm = B * (4 * D * h * w + 4 * Q * h * w) + 4 * Q * D
     achieved = bytes_decode / (decode_ms * 1e-3) / 1e9
-    pruned_path = args.decode in ("auto", "pruned") and H >= 4 * h and W >= 4 * w and Q >= 8 and token_mode(args) is not True
-    kname = "decode_pruned_kernel" if pruned_path else "decode_tiled_kernel"
-    # launches per step: contraction + decode (pruned path: champion pre-pass, pruned kernel, tiled kernel for the other images)
-    launches_per_step = 1 + ((2 if champs_written.value else 3) if args.decode in ("auto", "pruned") and H >= 4 * h and W >= 4 * w and Q >= 8 else 1)
+    cells_path = args.decode in ("auto", "cells") and H >= 4 * h and W >= 4 * w
+    kname = "decode_cells_kernel" if cells_path else ("decode_tiled_kernel" if args.decode != "generic" else "decode_generic_kernel")
+    launches_per_step = 2                       # contraction + decode
     line = {
         "metric": METRIC, "value": world * B * args.steps / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -407,7 +401,7 @@ def run_ours(args, cfg, rank, local, world):
         "config": {"workload": f"{args.workload}: {cfg['desc']}", "tokens": {True: "iid", False: "model-like (x2-upsampled coarse features)", "segmented": "segmented (piecewise-constant label regions + noise)"}[token_mode(args)],
                    "gt_dtype": "int64", "images_per_gpu_per_step": B, "parallelism": f"dp{world} (images sharded, one int64 all-reduce at the end)",
                    "contraction": {0: "fp32 FFMA", 1: "tcgen05 3xTF32", 2: "tcgen05 TF32 single pass"}[flags & 3],
-                   "decode": args.decode + (" (exact candidate pruning on finite, coherent images; tiled brute force on the rest)" if args.decode == "auto" else ""),
+                   "decode": args.decode + (" (exact per-cell candidate pruning, decode_cells_kernel)" if cells_path else ""),
                    "l2_policy": f"{n_sets} rotating input sets of {tok_bytes / 1e6:.0f} MB tokens each (> 126 MB L2 between reuses)"},
         "clocks": clocks,
         "e2e": e2e,

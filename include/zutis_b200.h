@@ -51,10 +51,10 @@ typedef enum {
     ZUTIS_DECODE_AUTO = 0,     /* fastest exact kernel the shape allows */
     ZUTIS_DECODE_GENERIC = 1,  /* one thread per output pixel, any scale/stride, NaN-exact */
     ZUTIS_DECODE_TILED = 2,    /* warp-tile kernel: low-res taps staged in shared memory */
-    ZUTIS_DECODE_PRUNED = 3,   /* warp-per-cell kernel with exact candidate pruning (needs a workspace) */
-    /* or-ed into the mode of zutis_decode_score_ws: the workspace already holds the champions of these logits
-     * (zutis_gemm_logits_champions reported champions_written = 1) */
-    ZUTIS_DECODE_CHAMPIONS_READY = 0x100
+    ZUTIS_DECODE_CELLS = 3,    /* exact per-cell candidate pruning: taps by TMA, one dominator per cell, survivor lists */
+    /* or-ed into the mode of zutis_decode_score_ws: the first 16 bytes of the workspace are zero (a fresh cudaMemset,
+     * or the workspace was last used by zutis_decode_score_ws, which leaves them zero), so no memset is enqueued */
+    ZUTIS_DECODE_WORKSPACE_ZEROED = 0x100
 } zutis_decode_mode;
 
 /* GEMM flags (bitwise or) */
@@ -97,21 +97,6 @@ ZUTIS_API int zutis_gemm_logits(const float* A, long lda, long strideA,
                                 int M, long N, int K, int batch, int flags,
                                 void* workspace, size_t workspace_bytes, void* stream);
 
-/* The same contraction, which additionally leaves in `decode_workspace` (>= zutis_decode_workspace_bytes) what the
- * candidate-pruning decode kernel needs per low-res pixel (first-max category = the low-res argmax, and its lead over
- * the categories with a smaller index) and per image (champion agreement of adjacent pixels, non-finite flag,
- * max |logit|), computed in the epilogue while the logits are still in registers.
- * img_w = low-res image width (N % img_w == 0).  *champions_written (host int, may be NULL) is set to 1 when the
- * by-product was produced (tensor-core path, <= 256 categories, no sigmoid); pass ZUTIS_DECODE_CHAMPIONS_READY in the
- * decode mode only in that case -- otherwise zutis_decode_score_ws computes the same data itself. */
-ZUTIS_API int zutis_gemm_logits_champions(const float* A, long lda, long strideA,
-                                          const float* Bm, long ldb, long strideB,
-                                          float* C, long stride_cn, long stride_cp, long strideC,
-                                          int M, long N, int K, int batch, int flags,
-                                          void* workspace, size_t workspace_bytes,
-                                          int img_w, void* decode_workspace, size_t decode_workspace_bytes,
-                                          int* champions_written, void* stream);
-
 /* ---------------------------------------------------------------------------------------------
  * (2)+(3)+(4) Fused bilinear upsample -> per-pixel argmax -> int16 labels -> confusion histogram.
  * Replaces F.interpolate(size, "bilinear") + torch.argmax(dim=1)   networks/zutis.py:366-372, trainer.py:169-173
@@ -133,14 +118,12 @@ ZUTIS_API int zutis_decode_score(const float* logits, long sb, long sq, long sy,
                                  int16_t* labels, int32_t* hist_partial, int n_classes,
                                  int mode, void* stream);
 
-/* Same contract with a caller-provided device workspace (>= zutis_decode_workspace_bytes, 8-byte aligned), which
- * enables the exact candidate-pruning kernel: per low-res cell only the categories that no corner champion dominates
- * at all four corner taps are interpolated (monotonicity of the bilinear expression, csrc/decode_pruned.cu).  Results
- * are identical to zutis_decode_score; ZUTIS_DECODE_AUTO sends each finite, spatially coherent image through the
- * pruned kernel and the others through the tiled kernel, ZUTIS_DECODE_PRUNED forces every finite image through it
- * (needs category index contiguous, sq == 1, 16-byte aligned pixels, >= 4x up-sampling and B <= 1024).  workspace ==
- * NULL behaves like zutis_decode_score.  The workspace is scratch: its content is consumed by the call (a
- * ZUTIS_DECODE_CHAMPIONS_READY workspace serves the decode of exactly the logits it was filled for). */
+/* Same contract with a caller-provided device workspace (>= zutis_decode_workspace_bytes, 8-byte aligned).  The
+ * per-cell pruning kernel (csrc/decode_cells.cu; ZUTIS_DECODE_AUTO picks it for pixel-major logits -- sq == 1,
+ * 16-byte aligned pixels -- and >= 4x up-sampling) then hands its work out through a global counter kept there, which
+ * balances the SMs; without a workspace it distributes cell rows statically.  Results are identical either way and
+ * identical to every other mode.  The kernel leaves the workspace zeroed; pass ZUTIS_DECODE_WORKSPACE_ZEROED when it
+ * is known to be zero and the call enqueues no memset.  workspace == NULL behaves like zutis_decode_score. */
 ZUTIS_API size_t zutis_decode_workspace_bytes(int B, int Q, int h, int w, int H, int W);
 ZUTIS_API int zutis_decode_score_ws(const float* logits, long sb, long sq, long sy, long sx,
                                     int B, int Q, int h, int w, int H, int W,

@@ -206,9 +206,9 @@ def _smooth_logits(B, Q, h, w, gen, contrast=1.0):
 
 @pytest.mark.parametrize("case", ["smooth", "smooth_noninteger", "x16", "x6", "iid", "ties", "nonfinite_mix", "wide", "wide_overflow", "hist_only", "uniform_regions", "near_ties"])
 def test_pruned_kernel_is_exact(zb, case):
-    """The candidate-pruning kernel must give the generic kernel's labels and histogram bit for bit -- on coherent
-    logits (where it prunes), on noise (where nearly everything survives), on exact ties and duplicated categories
-    (first maximum wins), and next to images with NaN/inf (which it must leave to the NaN-aware tiled kernel)."""
+    """The candidate-pruning (cell) kernel must give the generic kernel's labels and histogram bit for bit -- on coherent
+    logits (where it prunes), on noise (where nearly everything survives and lists overflow), on exact ties and
+    duplicated categories (first maximum wins), and on cells with NaN/inf taps (its NaN-aware brute-force path)."""
     from zutis_b200 import _ffi
     gen = torch.Generator().manual_seed(hash(case) % 1000 if False else len(case) * 7 + 1)
     want_labels = True
@@ -259,7 +259,7 @@ def test_pruned_kernel_is_exact(zb, case):
     ref = zb.ops.decode_score(t, (H, W), gt=gt.cuda(), hist_partial=ref_part, mode=_ffi.DECODE_GENERIC)
     if not case.startswith("wide"):
         assert np.array_equal(ref.cpu().numpy().astype(np.int64), O.c_decode_semantic(lo.numpy(), (H, W)))
-    for mode in (_ffi.DECODE_PRUNED, _ffi.DECODE_AUTO):
+    for mode in (_ffi.DECODE_CELLS, _ffi.DECODE_AUTO):
         part = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
         got = zb.ops.decode_score(t, (H, W), gt=gt.cuda(), hist_partial=part, mode=mode, want_labels=want_labels)
         if want_labels:
@@ -274,64 +274,60 @@ def test_pruned_kernel_is_exact(zb, case):
             want = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
             zb.ops.decode_score(t, (H, W), gt=g, hist_partial=want, mode=_ffi.DECODE_GENERIC, want_labels=False)
             part = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
-            zb.ops.decode_score(t, (H, W), gt=g, hist_partial=part, mode=_ffi.DECODE_PRUNED, want_labels=False)
-            assert torch.equal(part, want), f"histogram differs for {dt}"
+            zb.ops.decode_score(t, (H, W), gt=g, hist_partial=part, mode=_ffi.DECODE_CELLS, want_labels=False)
+            assert torch.equal(part, want), f"cell kernel: histogram differs for {dt}"
     # the pruned kernel needs contiguous categories; a query-major tensor must be refused in forced mode, not mis-read
     with pytest.raises(zb.ZutisUnsupported):
-        zb.ops.decode_score(lo.cuda(), (H, W), mode=_ffi.DECODE_PRUNED)
+        zb.ops.decode_score(lo.cuda(), (H, W), mode=_ffi.DECODE_CELLS)
     assert torch.equal(zb.ops.decode_score(lo.cuda(), (H, W)), ref)
 
 
-def test_contraction_epilogue_champions_equal_decode_prepass(zb):
-    """zutis_gemm_logits_champions must leave in the workspace what the decode kernel's own pre-pass computes
-    (same champions, non-finite flags, and an agreement count on the same side of the threshold), and
-    decode_and_score must use it and still match the generic kernel bit for bit."""
+def test_cell_kernel_work_distribution_and_workspace(zb):
+    """The cell kernel hands out its runs through a global counter when it gets a workspace (dynamic) and by cell rows
+    otherwise (static): same labels and histogram, the workspace is left zeroed, a dirty workspace is re-armed unless
+    the caller vouches for it, in-place changes of the logits are seen, and decode_and_score matches the generic kernel."""
+    import ctypes as C
     from zutis_b200 import _ffi
     gen = torch.Generator().manual_seed(3)
     B, Q, D, h, w, H, W = 5, 81, 512, 20, 24, 160, 192
     text = torch.nn.functional.normalize(torch.randn(Q, D, generator=gen), dim=-1).cuda()
     coarse = torch.randn(B, D, h // 2, w // 2, generator=gen)
     tokens = torch.nn.functional.normalize(torch.nn.functional.interpolate(coarse, scale_factor=2, mode="bilinear").permute(0, 2, 3, 1), dim=-1).contiguous().cuda()
-    tokens[3] = torch.nn.functional.normalize(torch.randn(h, w, D, generator=gen), dim=-1).cuda()     # an incoherent image -> tiled kernel
-    tokens[4, 2, 3, 7] = float("nan")                                                                  # a non-finite image -> tiled kernel
+    tokens[3] = torch.nn.functional.normalize(torch.randn(h, w, D, generator=gen), dim=-1).cuda()     # an incoherent image: long lists, overflow
+    tokens[4, 2, 3, 7] = float("nan")                                                                  # a poisoned pixel: brute-force cells
     gt = torch.randint(0, Q, (B, H, W), generator=gen).cuda()
-    ws = zb.ops.DecodeWorkspace()
-    lo = zb.ops.contraction(text, tokens, precision="tf32x3", decode_ws=ws)
-    assert ws.ready_for == (lo.data_ptr(), (B, Q, h, w), lo._version)
-    n = B * h * w                                                   # workspace: champions [n] int32 | leads [n] fp32 | counters [3*B] int32
-    assert n % 2 == 0
-    champ_gemm = ws.buf[: n * 4].view(torch.int32).clone()
-    lead_gemm = ws.buf[n * 4: n * 8].view(torch.float32).clone()
-    stats_gemm = ws.buf[n * 8: n * 8 + 12 * B].view(torch.int32).clone()
-    part = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
-    got = zb.ops.decode_score(lo, (H, W), gt=gt, hist_partial=part, workspace=ws)                      # READY path
-    ws2 = zb.ops.DecodeWorkspace()
-    part2 = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
-    got2 = zb.ops.decode_score(lo, (H, W), gt=gt, hist_partial=part2, workspace=ws2)                   # own pre-pass
-    champ_own = ws2.buf[: n * 4].view(torch.int32)
-    lead_own = ws2.buf[n * 4: n * 8].view(torch.float32)
-    stats_own = ws2.buf[n * 8: n * 8 + 12 * B].view(torch.int32)
-    finite = (stats_own[B:2 * B] == 0).repeat_interleave(h * w)
-    assert torch.equal(champ_gemm[finite], champ_own[finite])
-    assert torch.equal(lead_gemm[finite], lead_own[finite])
-    flat = lo.permute(0, 2, 3, 1).reshape(n, Q)                      # lead = champion - best of the categories in front of it
-    before = torch.where(torch.arange(Q, device="cuda")[None, :] < champ_own[:, None].long(), flat, torch.full_like(flat, float("-inf"))).amax(dim=1)
-    want_lead = flat.gather(1, champ_own[:, None].long())[:, 0] - before
-    assert torch.equal(lead_own[finite], want_lead[finite])
-    assert torch.equal(stats_gemm[B:2 * B] != 0, stats_own[B:2 * B] != 0) and stats_own[B:2 * B].tolist() == [0, 0, 0, 0, 1]
-    assert torch.equal(stats_gemm[2 * B:3 * B - 1], stats_own[2 * B:3 * B - 1])                      # bits of max |logit| per finite image
-    assert torch.equal(stats_own[2 * B:3 * B - 1].view(torch.float32), lo[:4].abs().amax(dim=(1, 2, 3)))
-    thr = (h * (w - 1) + 9) // 10
-    assert torch.equal(stats_gemm[:B] >= thr, stats_own[:B] >= thr) and (stats_own[:4] >= thr).tolist() == [True, True, True, False]
+    lo = zb.ops.contraction(text, tokens, precision="tf32x3")
     ref_part = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
     ref = zb.ops.decode_score(lo, (H, W), gt=gt, hist_partial=ref_part, mode=_ffi.DECODE_GENERIC)
-    assert torch.equal(got, ref) and torch.equal(got2, ref) and torch.equal(part, ref_part) and torch.equal(part2, ref_part)
-    # logits changed in place after the contraction: the stale champions must not be trusted
-    ws3 = zb.ops.DecodeWorkspace()
-    lo3 = zb.ops.contraction(text, tokens, precision="tf32x3", decode_ws=ws3)
+    lib = _ffi.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def raw(ws, mode):
+        labels = torch.empty(B, H, W, dtype=torch.int16, device="cuda")
+        part = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
+        args = (lo.data_ptr(), lo.stride(0), lo.stride(1), lo.stride(2), lo.stride(3), B, Q, h, w, H, W, gt.data_ptr(), _ffi.GT_I64, H * W,
+                labels.data_ptr(), part.data_ptr(), Q)
+        if ws is None:
+            _ffi.check(lib.zutis_decode_score(*args, mode, stream))
+        else:
+            _ffi.check(lib.zutis_decode_score_ws(*args, mode, ws.data_ptr(), ws.numel(), stream))
+        return labels, part
+
+    assert lib.zutis_decode_workspace_bytes(B, Q, h, w, H, W) == 16
+    for ws, mode in ((None, _ffi.DECODE_CELLS),                                                      # static rows
+                     (torch.zeros(16, dtype=torch.uint8, device="cuda"), _ffi.DECODE_CELLS | _ffi.DECODE_WORKSPACE_ZEROED),
+                     (torch.full((16,), 0xAB, dtype=torch.uint8, device="cuda"), _ffi.DECODE_AUTO)):   # dirty: the call re-arms it
+        for _ in range(3):                                                                           # the workspace is reusable
+            labels, part = raw(ws, mode)
+            assert torch.equal(labels, ref) and torch.equal(part, ref_part)
+            if ws is not None:
+                assert int(ws.view(torch.int32).abs().sum()) == 0
+            mode |= _ffi.DECODE_WORKSPACE_ZEROED if ws is not None else 0
+    # logits changed in place after the contraction are simply decoded as they are
+    lo3 = zb.ops.contraction(text, tokens, precision="tf32x3")
     lo3[:, 5] += 1.0
     want3 = zb.ops.decode_score(lo3, (H, W), mode=_ffi.DECODE_GENERIC)
-    assert torch.equal(zb.ops.decode_score(lo3, (H, W), workspace=ws3), want3)
+    assert torch.equal(zb.ops.decode_score(lo3, (H, W), workspace=zb.ops.DecodeWorkspace()), want3)
     meter = zb.RunningScore(Q)
     labels = zb.decode_and_score(text, tokens, gt, (H, W), meter, want_labels=True, precision="tf32x3")
     assert torch.equal(labels, ref) and torch.equal(meter.counts().view(-1).to(torch.int32), ref_part)

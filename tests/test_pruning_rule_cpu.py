@@ -1,7 +1,7 @@
-"""The candidate-pruning rule of csrc/decode_pruned.cu, restated in numpy float32 and checked against the CPU oracle's
-exact labels: on every cell, the label of every pixel must be among the categories the rule keeps, and a cell that
-qualifies for the whole-cell shortcut must carry its champion everywhere.  No GPU needed: this pins the argument
-(monotone rounding + margin) independently of the kernel that implements it."""
+"""The candidate-pruning rule of csrc/decode_cells.cu, restated in numpy float32 and checked against the CPU oracle's
+exact labels: on every cell, the label of every pixel must be among the categories the rule keeps, a cell whose list
+holds a single category must carry it everywhere, and ANY category may serve as dominator without losing a winner.
+No GPU needed: this pins the argument (monotone rounding + margin) independently of the kernel that implements it."""
 import numpy as np
 import pytest
 
@@ -15,35 +15,19 @@ def _cells(n_in, n_out):
     return starts
 
 
-def _survivors(A, B, C, D, margin):
-    """float32 restatement of the dominance test: keep q unless some corner champion k leads it at all four corners,
-    by >= 0 when k < q and by >= margin when k >= q."""
-    Q = A.shape[0]
+def _dominator(A, B, C, D):
+    """k* = argmax_q min_corner L_q (first such q): the category with the best guaranteed value in the cell"""
+    return int(np.argmax(np.minimum.reduce([A, B, C, D])))
+
+
+def _survivors(A, B, C, D, k):
+    """float32 restatement of the test: keep q unless dominator k leads it at all four corners by
+    m = 2^-20 * max_c |K_c| (never 0), the differences rounded to fp32 like the kernel's fma(q, -1, K)."""
     corners = (A, B, C, D)
-    champs = []
-    for X in corners:
-        k = int(np.argmax(X))                       # first maximum
-        if k not in champs:
-            champs.append(k)
-    keep = np.ones(Q, bool)
-    q = np.arange(Q)
-    for k in champs:
-        lead = np.minimum.reduce([np.float32(X[k]) - X for X in corners]).astype(np.float32)   # RN(champion - q), fp32
-        thr = np.where(k < q, np.float32(0), margin).astype(np.float32)
-        keep &= ~(lead >= thr)
-    return keep, champs
-
-
-def _shortcut(A, B, C, D, margin):
-    ks = {int(np.argmax(X)) for X in (A, B, C, D)}
-    if len(ks) != 1:
-        return None
-    k = ks.pop()
-    for X in (A, B, C, D):
-        before = X[:k].max() if k > 0 else np.float32(-np.inf)
-        if not (np.float32(X[k] - before) >= margin):
-            return None
-    return k
+    K = [np.float32(X[k]) for X in corners]
+    margin = np.float32(max(np.float32(max(abs(v) for v in K)) * np.float32(2.0 ** -20), np.float32(1e-37)))
+    lead = np.minimum.reduce([(Kc - X).astype(np.float32) for Kc, X in zip(K, corners)])
+    return ~(lead >= margin)
 
 
 @pytest.mark.parametrize("case", ["smooth", "noise", "near_ties", "duplicates", "regions", "noninteger"])
@@ -74,8 +58,7 @@ def test_pruning_rule_never_drops_the_winner(case):
         lo[region, np.arange(h)[:, None], np.arange(w)[None, :]] += 1.0
     labels = O.c_decode_semantic(lo[None], (H, W))[0]
     ys, xs = _cells(h, H), _cells(w, W)
-    margin = np.float32(max(np.float32(np.abs(lo).max()) * np.float32(2.0 ** -20), np.float32(1e-37)))
-    kept_total, shortcuts = 0, 0
+    kept_total, singles = 0, 0
     for cy in range(h):
         for cx in range(w):
             cy1, cx1 = min(cy + 1, h - 1), min(cx + 1, w - 1)
@@ -83,15 +66,19 @@ def test_pruning_rule_never_drops_the_winner(case):
             cell = labels[ys[cy]:ys[cy + 1], xs[cx]:xs[cx + 1]]
             if cell.size == 0:
                 continue
-            keep, _ = _survivors(A, B, C, D, margin)
+            k = _dominator(A, B, C, D)
+            keep = _survivors(A, B, C, D, k)
+            assert keep[k]                                              # the dominator never drops itself
             assert keep[np.unique(cell)].all(), (case, cy, cx, np.unique(cell), np.flatnonzero(keep))
             kept_total += int(keep.sum())
-            k = _shortcut(A, B, C, D, margin)
-            if k is not None:
-                shortcuts += 1
+            if keep.sum() == 1:
+                singles += 1
                 assert (cell == k).all(), (case, cy, cx, k, np.unique(cell))
+            # which category dominates only changes how much is pruned, never whether a winner survives
+            for other in (0, Q - 1, int(rng.integers(0, Q))):
+                assert _survivors(A, B, C, D, other)[np.unique(cell)].all(), (case, cy, cx, other)
     assert kept_total >= h * w                                          # at least the winner survives everywhere
     if case == "regions":
-        assert shortcuts > 0                                            # the shortcut is exercised
+        assert singles > 0                                              # single-survivor cells are exercised
     if case == "smooth":
         assert kept_total < 0.5 * Q * h * w                             # and the rule actually prunes

@@ -16,15 +16,14 @@ flags = _ffi.GEMM_TF32X3
 ws_bytes = lib.zutis_gemm_workspace_bytes(Q, h * w, D, B, flags)
 ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
 dws_bytes = lib.zutis_decode_workspace_bytes(B, Q, h, w, H, W)
-dws = torch.empty(dws_bytes, dtype=torch.uint8, device="cuda")
+dws = torch.zeros(dws_bytes, dtype=torch.uint8, device="cuda")
 stream = torch.cuda.current_stream().cuda_stream
-written = ctypes.c_int(0)
 def gemm(fl):
-    _ffi.check(lib.zutis_gemm_logits_champions(text.data_ptr(), D, 0, tokens.data_ptr(), D, h * w * D, logits.data_ptr(), 1, Qp, h * w * Qp,
-                                               Q, h * w, D, B, fl, ws.data_ptr(), ws_bytes, w, dws.data_ptr(), dws_bytes, ctypes.addressof(written), stream))
+    _ffi.check(lib.zutis_gemm_logits(text.data_ptr(), D, 0, tokens.data_ptr(), D, h * w * D, logits.data_ptr(), 1, Qp, h * w * Qp,
+                                     Q, h * w, D, B, fl, ws.data_ptr(), ws_bytes, stream))
 def decode():
     _ffi.check(lib.zutis_decode_score_ws(logits.data_ptr(), h * w * Qp, 1, w * Qp, Qp, B, Q, h, w, H, W, gt.data_ptr(), _ffi.GT_I64, H * W,
-                                         labels.data_ptr(), part.data_ptr(), Q, _ffi.DECODE_AUTO | (_ffi.DECODE_CHAMPIONS_READY if written.value else 0),
+                                         labels.data_ptr(), part.data_ptr(), Q, _ffi.DECODE_AUTO | _ffi.DECODE_WORKSPACE_ZEROED,
                                          dws.data_ptr(), dws_bytes, stream))
 gemm(flags); decode(); torch.cuda.synchronize()
 fl = flags | _ffi.GEMM_A_PREPARED

@@ -11,17 +11,21 @@ lo = ops.contraction(text, tok_big)                         # tcgen05, multi-rou
 lo2 = ops.contraction(text, tokens, precision="fp32")      # SIMT
 meter = zutis_b200.RunningScore(81)
 labels = zutis_b200.decode_and_score(text, tokens, gt, (224, 224), meter, want_labels=True)
-ops.decode_score(lo[:2], (320, 320))                        # AUTO: champion pre-pass, pruned or tiled per image
+ops.decode_score(lo[:2], (320, 320))                        # AUTO: the cell kernel (TMA-staged taps)
 from zutis_b200 import _ffi
 coarse = torch.randn(3, 81, 6, 6, device="cuda")
 smooth = torch.nn.functional.interpolate(coarse, size=(20, 20), mode="bilinear")
 pm = torch.zeros(3, 20, 20, 84, device="cuda"); pm[..., :81] = smooth.permute(0, 2, 3, 1)
 part = torch.zeros(81 * 81, dtype=torch.int32, device="cuda")
 ops.decode_score(pm[..., :81].permute(0, 3, 1, 2), (160, 160), gt=torch.randint(0, 81, (3, 160, 160), device="cuda"),
-                 hist_partial=part, mode=_ffi.DECODE_PRUNED)  # pruned kernel forced, with histogram
+                 hist_partial=part, mode=_ffi.DECODE_CELLS)   # cell kernel forced, with histogram
 ws = ops.DecodeWorkspace()
-lo3 = ops.contraction(text, tok_big[:3], decode_ws=ws)      # champions from the contraction epilogue
+lo3 = ops.contraction(text, tok_big[:3])
 ops.decode_score(lo3, (320, 320), workspace=ws)
+wide = torch.nn.functional.interpolate(torch.randn(1, 300, 4, 4, device="cuda"), size=(9, 10), mode="bilinear")
+pw = torch.zeros(1, 9, 10, 300, device="cuda"); pw.copy_(wide.permute(0, 2, 3, 1))
+ops.decode_score(pw.permute(0, 3, 1, 2), (72, 80), mode=_ffi.DECODE_CELLS)     # wide Q: taps from global memory
+ops.decode_score(lo[:1], (320, 320), mode=_ffi.DECODE_TILED)
 ops.decode_score(lo2, (100, 90), mode=1)
 meter.update(gt, labels); meter.get_scores()
 probs = torch.sigmoid(3 * torch.randn(2, 100, 15, 20, device="cuda"))

@@ -16,8 +16,8 @@ LIB_PATH = os.path.join(_HERE, "libzutis_b200.so")
 
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE, ERR_NO_DEVICE = range(6)
 GT_U8, GT_I16, GT_I32, GT_I64 = range(4)
-DECODE_AUTO, DECODE_GENERIC, DECODE_TILED, DECODE_PRUNED = range(4)
-DECODE_CHAMPIONS_READY = 0x100
+DECODE_AUTO, DECODE_GENERIC, DECODE_TILED, DECODE_CELLS = range(4)
+DECODE_WORKSPACE_ZEROED = 0x100
 GEMM_FP32_SIMT, GEMM_TF32X3, GEMM_TF32 = 0, 1, 2
 GEMM_SIGMOID = 16
 GEMM_A_PREPARED = 32
@@ -48,7 +48,6 @@ SIGNATURES = {
     "zutis_device_check": (_i, [_i]),
     "zutis_gemm_workspace_bytes": (_sz, [_i, _l, _i, _i, _i]),
     "zutis_gemm_logits": (_i, [_vp, _l, _l, _vp, _l, _l, _vp, _l, _l, _l, _i, _l, _i, _i, _i, _vp, _sz, _vp]),
-    "zutis_gemm_logits_champions": (_i, [_vp, _l, _l, _vp, _l, _l, _vp, _l, _l, _l, _i, _l, _i, _i, _i, _vp, _sz, _i, _vp, _sz, _vp, _vp]),
     "zutis_decode_score": (_i, [_vp, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _vp, _i, _l, _vp, _vp, _i, _i, _vp]),
     "zutis_decode_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "zutis_decode_score_ws": (_i, [_vp, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _vp, _i, _l, _vp, _vp, _i, _i, _vp, _sz, _vp]),

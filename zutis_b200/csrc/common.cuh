@@ -109,18 +109,6 @@ __device__ __forceinline__ void warp_hist_add(int* hist, int key) {
 }
 #endif
 
-// workspace of the pruned decode path (zutis_decode_workspace_bytes), n = B*h*w rounded up to even:
-//   champions [n] int    first-max category per low-res pixel
-//   leads     [n] float  champion's value minus the largest value of a category with a SMALLER index (+inf if none)
-//   counters  [3*B] int  per image: adjacent-champion agreements, non-finite flag, bits of max |logit|
-//             (non-negative floats order like ints) | 1 int: work counter of the pruned kernel.
-// Everything behind the leads is zeroed by whoever fills the champions.
-inline size_t decode_ws_bytes(long B, long hw) { return (size_t)((B * hw + 1) & ~1L) * 8 + (size_t)(3 * B + 1) * 4; }
-inline size_t decode_ws_counter_bytes(long B) { return (size_t)(3 * B + 1) * 4; }
-inline int* decode_ws_champ(void* ws) { return reinterpret_cast<int*>(ws); }
-inline float* decode_ws_lead(void* ws, long B, long hw) { return reinterpret_cast<float*>(ws) + ((B * hw + 1) & ~1L); }
-inline int* decode_ws_stats(void* ws, long B, long hw) { return reinterpret_cast<int*>(ws) + 2 * ((B * hw + 1) & ~1L); }
-
 inline int gt_dtype_bytes(int dtype) {
     switch (dtype) {
         case ZUTIS_GT_U8: return 1;

@@ -1,5 +1,5 @@
 // Shared declarations of the decode kernels (decode_score.cu: generic + tiled + threshold kernels and the dispatcher;
-// decode_pruned.cu: champion pass and the candidate-pruning kernel).
+// decode_cells.cu: the per-cell candidate-pruning kernel).
 #pragma once
 #include "common.cuh"
 
@@ -27,22 +27,7 @@ struct DecodeParams {
     int vec_stage;   // taps can be staged with 16-byte cp.async (category index contiguous and aligned)
     int gt_bytes;    // sizeof one ground-truth label
     long n_items;    // B * n_groups * XB
-    // image selection between the tiled and the pruned kernel (workspace path only)
-    int select;              // 0: every image; 1: images the pruned kernel does NOT take; 2: images it takes
-    int agree_min;           // an image is pruned when it is finite and >= agree_min neighbouring low-res pixels share their champion
-    int* img_stats;          // [B] neighbour agreements | [B] non-finite flags | [B] bits of max |logit| (champion_kernel) | work counter
-    const int* champ;        // [B*h*w] first-max category per low-res pixel
-    const float* lead;       // [B*h*w] its value minus the largest value of a category with a smaller index
-    long lead_delta;         // lead - champ in 4-byte elements
-    int cap;                 // candidate slots per warp in the pruned kernel
-    // byte offsets of the pruned kernel's tables in dynamic shared memory (computed by the host so that the kernel can
-    // re-derive a pointer with one add instead of a chain of size computations when registers run out)
-    int off_ystart, off_xstart, off_ly, off_lx, off_img, off_warp;
 };
-
-__device__ __forceinline__ bool image_is_pruned(const DecodeParams& p, int b) {
-    return p.img_stats[p.B + b] == 0 && p.img_stats[b] >= p.agree_min;
-}
 
 // smallest d in [0,out] whose first tap index is >= target
 __device__ __forceinline__ int first_dst_with_tap_ge(int target, int in, int out, float scale) {
@@ -87,21 +72,6 @@ __device__ __forceinline__ int class_of(GT g, int n) {
     return (g >= (GT)0 && (long long)g < (long long)n) ? (int)g : -1;
 }
 
-// the images this kernel owns, in ascending order (select: 1 = not pruned, 2 = pruned); one warp, B <= 1024
-__device__ __forceinline__ void build_image_list(const DecodeParams& p, int want_pruned, int* s_img, int* s_nimg) {
-    if (threadIdx.x < 32) {
-        int n = 0;
-        for (int b0 = 0; b0 < p.B; b0 += 32) {
-            const int b = b0 + (int)threadIdx.x;
-            const bool mine = b < p.B && (image_is_pruned(p, b) == (want_pruned != 0));
-            const unsigned bal = __ballot_sync(0xffffffffu, mine);
-            if (mine) s_img[n + __popc(bal & ((1u << threadIdx.x) - 1u))] = b;
-            n += __popc(bal);
-        }
-        if (threadIdx.x == 0) *s_nimg = n;
-    }
-}
-
 // Add a CTA's shared-memory histogram into the global int32 partial.  Two neighbouring bins travel in ONE 64-bit atomic
 // when the partial is 8-byte aligned: counts are non-negative and the whole partial stays below 2^31 (the entry point
 // checks B*H*W), so the low word never carries into the high one.  All CTAs flush at about the same time, which makes
@@ -124,11 +94,9 @@ __device__ __forceinline__ void flush_shared_hist(const int* s_hist, int* hist, 
     }
 }
 
-// decode_pruned.cu.  Sets up and launches the pruned kernel (and the champion pass unless the workspace already
-// holds the champions of these logits) for the images it owns; on success *launched = true and p.select = 1, so that
-// the tiled kernel launched next takes the remaining images.  forced = ZUTIS_DECODE_PRUNED (every finite image).
-// *launched = false with ZUTIS_OK means "does not fit, use the tiled kernel alone" (only when not forced).
-int launch_decode_pruned(DecodeParams& p, bool forced, bool champions_ready, int label_dtype, void* workspace, int sms,
-                         cudaStream_t stream, bool* launched);
+// decode_cells.cu: the per-cell pruning kernel.  counter: two zeroed words of workspace for dynamic work distribution
+// (NULL: static).  *launched = false with ZUTIS_OK means "shape not taken, use another kernel" (only when not forced).
+int launch_decode_cells(const DecodeParams& p, bool forced, int label_dtype, unsigned* counter, int sms, cudaStream_t stream,
+                        bool* launched);
 
 }  // namespace zutis

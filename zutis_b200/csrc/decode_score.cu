@@ -4,8 +4,8 @@
 //   F.interpolate(lo, size, "bilinear") ; torch.argmax(dim=1)     networks/zutis.py:366-372
 //   RunningScore._fast_hist                                        utils/running_score.py:10-16
 //
-// Three kernels (the third, decode_pruned_kernel with exact candidate pruning, lives in decode_pruned.cu; the
-// dispatcher at the end of this file splits the images between it and the tiled kernel):
+// Three kernels (the third, decode_cells_kernel with exact per-cell candidate pruning, lives in decode_cells.cu and is
+// what ZUTIS_DECODE_AUTO picks for pixel-major logits and >= 4x up-sampling; the dispatcher is at the end of this file):
 //   decode_generic_kernel : one thread per output pixel, taps read straight from global memory.
 //                           Any scale (also down-sampling), any strides, identity (size=None),
 //                           NaN-exact.  The always-correct path.
@@ -199,19 +199,7 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const
     float2* s_ly = reinterpret_cast<float2*>(s_groups + p.n_groups);             // [H]: (ly0, ly1)
     const int row_stride = p.XR * p.QS;                                          // floats between the two staged rows
     const int tile_floats = 2 * row_stride;
-    int* s_img = reinterpret_cast<int*>(s_ly + ((p.H + 1) & ~1));                // [B] images of this launch (select != 0)
-    float* tiles = reinterpret_cast<float*>(s_img + (p.select ? ((p.B + 3) & ~3) : 0)) + warp * (2 * tile_floats);
-    __shared__ int s_nimg;
-
-    // ---- which images are ours (the pruned kernel takes the finite, spatially coherent ones)
-    if (p.select) {
-        // this launch follows the pruned kernel on the stream: re-arm its work counter so that the same workspace
-        // (champions included) can serve another decode of the same logits
-        if (blockIdx.x == 0 && threadIdx.x == 0) p.img_stats[3 * p.B] = 0;
-        build_image_list(p, p.select == 2, s_img, &s_nimg);
-        __syncthreads();
-        if (s_nimg == 0) return;
-    }
+    float* tiles = reinterpret_cast<float*>(s_ly + ((p.H + 1) & ~1)) + warp * (2 * tile_floats);
 
     // ---- per-CTA tables
     for (int i = threadIdx.x; i < nn && p.hist_in_smem; i += blockDim.x) s_hist[i] = 0;
@@ -237,7 +225,7 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const
     // (32-bit index math: the host guarantees n_items * nchunk < 2^31 and per-image offsets < 2^31)
     const unsigned first_item = blockIdx.x * kTiledWarps + warp;
     const unsigned item_stride = gridDim.x * kTiledWarps;
-    const unsigned total_items = p.select ? (unsigned)s_nimg * (unsigned)p.n_groups * (unsigned)p.XB : (unsigned)p.n_items;
+    const unsigned total_items = (unsigned)p.n_items;
     const unsigned my_items = first_item < total_items ? (total_items - first_item + item_stride - 1) / item_stride : 0;
     const unsigned n_units = my_items * nchunk;
     const int sx = (int)p.sx, sy = (int)p.sy, sq = (int)p.sq;
@@ -251,7 +239,6 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2) decode_tiled_kernel(const
         const unsigned t = item / (unsigned)p.XB;
         const int4 grp = s_groups[t % (unsigned)p.n_groups];
         un.b = (int)(t / (unsigned)p.n_groups);
-        if (p.select) un.b = s_img[un.b];
         un.cy = grp.x; un.Y0 = grp.y; un.nr = grp.z;
         un.rx_lo = axis_tap(un.xb * 32, p.w, p.W, p.scale_x).i0;
         return un;
@@ -655,13 +642,10 @@ int launch_threshold_tiled(const float* probs, long sb, long sq, long sy, long s
 
 using namespace zutis;
 
-// workspace of the pruned path: champions [B*h*w] int2 | per-image counters [2*B] int
-static size_t decode_workspace_bytes(int B, int h, int w) { return decode_ws_bytes(B, (long)h * w); }
-
+// workspace of the cell kernel: its global run counter and the finished-CTA count (two words, 16 bytes reserved)
 extern "C" size_t zutis_decode_workspace_bytes(int B, int Q, int h, int w, int H, int W) {
-    (void)Q; (void)H; (void)W;
-    if (B <= 0 || h <= 0 || w <= 0) return 0;
-    return decode_workspace_bytes(B, h, w);
+    (void)B; (void)Q; (void)h; (void)w; (void)H; (void)W;
+    return 16;
 }
 
 static int decode_score_impl(const float* logits, long sb, long sq, long sy, long sx,
@@ -670,9 +654,9 @@ static int decode_score_impl(const float* logits, long sb, long sq, long sy, lon
                              int16_t* labels, int32_t* hist_partial, int n_classes,
                              int mode, void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    // the contraction may have left the champions in the workspace already (zutis_gemm_logits_champions)
-    const bool champions_ready = (mode & ZUTIS_DECODE_CHAMPIONS_READY) != 0;
-    mode &= ~ZUTIS_DECODE_CHAMPIONS_READY;
+    // the caller may promise that the workspace words are zero (fresh cudaMemset, or last used by this entry point)
+    const bool workspace_zeroed = (mode & ZUTIS_DECODE_WORKSPACE_ZEROED) != 0;
+    mode &= ~ZUTIS_DECODE_WORKSPACE_ZEROED;
     ZUTIS_REQUIRE(logits != nullptr, "zutis_decode_score: logits is NULL");
     ZUTIS_REQUIRE(B > 0 && Q > 0 && h > 0 && w > 0 && H > 0 && W > 0,
                   "zutis_decode_score: non-positive shape B=%d Q=%d h=%d w=%d H=%d W=%d", B, Q, h, w, H, W);
@@ -685,7 +669,7 @@ static int decode_score_impl(const float* logits, long sb, long sq, long sy, lon
         ZUTIS_REQUIRE(gt_sb >= (long)H * W || B == 1, "zutis_decode_score: gt_sb=%ld smaller than H*W", gt_sb);
     }
     ZUTIS_REQUIRE(labels != nullptr || hist_partial != nullptr, "zutis_decode_score: nothing to produce (labels and hist_partial both NULL)");
-    ZUTIS_REQUIRE(mode >= ZUTIS_DECODE_AUTO && mode <= ZUTIS_DECODE_PRUNED, "zutis_decode_score: bad mode %d", mode);
+    ZUTIS_REQUIRE(mode >= ZUTIS_DECODE_AUTO && mode <= ZUTIS_DECODE_CELLS, "zutis_decode_score: bad mode %d", mode);
     int st = current_device_ok();
     if (st != ZUTIS_OK) return st;
 
@@ -697,8 +681,6 @@ static int decode_score_impl(const float* logits, long sb, long sq, long sy, lon
     p.labels = labels; p.hist = hist_partial; p.n = hist_partial ? n_classes : 1;
     p.identity = (H == h && W == w);
     p.XB = (W + 31) / 32; p.XR = 0; p.QC = 0; p.QS = 0; p.hist_in_smem = 0; p.n_items = 0; p.n_groups = 0; p.vec_stage = 0; p.gt_bytes = gt ? gt_dtype_bytes(gt_dtype) : 0;
-    p.select = 0; p.agree_min = 0; p.img_stats = nullptr; p.champ = nullptr; p.lead = nullptr; p.lead_delta = 0; p.cap = 0;
-    p.off_ystart = p.off_xstart = p.off_ly = p.off_lx = p.off_img = p.off_warp = 0;
 
     const int sms = sm_count();
 
@@ -716,17 +698,26 @@ static int decode_score_impl(const float* logits, long sb, long sq, long sy, lon
     }
     if (mode == ZUTIS_DECODE_TILED && !tiled_ok)
         return fail(ZUTIS_ERR_UNSUPPORTED, "zutis_decode_score: tiled kernel needs up-sampling with <= 8 low-res columns per 32 outputs");
-    // ---- can the pruned kernel take the coherent images?  (category index contiguous, cells of >= 4x4 pixels, workspace)
-    const size_t ws_need = decode_workspace_bytes(B, h, w);
     const long extent_px = (long)(h - 1) * sy + (long)(w - 1) * sx + (long)(Q - 1);
-    bool pruned_ok = tiled_ok && sq == 1 && sx > 0 && sy > 0 && H >= 4 * h && W >= 4 * w && Q >= 8 && B <= 1024 &&
-                     extent_px < 2147483647L && (long)B * h * w < 2147483647L && workspace != nullptr && workspace_bytes >= ws_need &&
-                     (reinterpret_cast<uintptr_t>(workspace) & 7) == 0 && w <= 8192 &&
-                     (sx & 3) == 0 && (sy & 3) == 0 && (sb & 3) == 0 && sx >= ((Q + 3) & ~3) && (reinterpret_cast<uintptr_t>(logits) & 15) == 0;
-    if (mode == ZUTIS_DECODE_PRUNED && !pruned_ok)
-        return fail(ZUTIS_ERR_UNSUPPORTED, "zutis_decode_score: pruned kernel needs contiguous categories, >= 4x up-sampling, B <= 1024 and a workspace of %zu bytes (zutis_decode_workspace_bytes)", ws_need);
-    const bool use_pruned = pruned_ok && (mode == ZUTIS_DECODE_PRUNED || mode == ZUTIS_DECODE_AUTO);
-    const bool use_tiled = use_pruned || (mode == ZUTIS_DECODE_TILED) || (mode == ZUTIS_DECODE_AUTO && tiled_ok);
+    // ---- cell kernel: exact per-cell pruning; pixel-major logits (category index contiguous, 16-byte aligned pixels) and
+    // cells of >= 4x4 output pixels.  No workspace, every image (non-finite taps take its brute-force path).
+    const bool cells_ok = !p.identity && sq == 1 && sx > 0 && sy > 0 && H >= 4 * h && W >= 4 * w && Q >= 2 && Q <= 65535 &&
+                          extent_px < 2147483647L && (sx & 3) == 0 && (sy & 3) == 0 && (sb & 3) == 0 && sx >= ((Q + 3) & ~3) &&
+                          (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && H <= 16384 && W <= 16384;
+    if (mode == ZUTIS_DECODE_CELLS && !cells_ok)
+        return fail(ZUTIS_ERR_UNSUPPORTED, "zutis_decode_score: cell kernel needs contiguous categories with 16-byte aligned pixels and >= 4x up-sampling");
+    if (cells_ok && (mode == ZUTIS_DECODE_CELLS || mode == ZUTIS_DECODE_AUTO)) {
+        // with a workspace the runs are handed out through a global counter (dynamic balance over the SMs)
+        unsigned* counter = nullptr;
+        if (workspace && workspace_bytes >= 16 && (reinterpret_cast<uintptr_t>(workspace) & 7) == 0) {
+            counter = reinterpret_cast<unsigned*>(workspace);
+            if (!workspace_zeroed) ZUTIS_CUDA(cudaMemsetAsync(counter, 0, 16, stream));
+        }
+        bool launched = false;
+        st = launch_decode_cells(p, mode == ZUTIS_DECODE_CELLS, hist_partial ? gt_dtype : ZUTIS_GT_I64, counter, sms, stream, &launched);
+        if (st != ZUTIS_OK || launched) return st;
+    }
+    const bool use_tiled = (mode == ZUTIS_DECODE_TILED) || (mode == ZUTIS_DECODE_AUTO && tiled_ok);
 
     if (use_tiled) {
         p.XR = XR;
@@ -751,21 +742,13 @@ static int decode_score_impl(const float* logits, long sb, long sq, long sy, lon
         p.vec_stage = (sq == 1) && ((sx & 3) == 0) && ((sy & 3) == 0) && ((sb & 3) == 0) && (sx >= ((Q + 3) & ~3)) &&
                       ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
         const size_t smem = (size_t)(p.hist_in_smem ? ((nn + 3) & ~3) : 0) * 4 + (size_t)((h + 1 + 3) & ~3) * 4 + (size_t)groups * 16 +
-                            (size_t)((H + 1) & ~1) * 8 + (size_t)kTiledWarps * 2 * 2 * XR * p.QS * 4 + (use_pruned ? (size_t)((B + 3) & ~3) * 4 : 0);
+                            (size_t)((H + 1) & ~1) * 8 + (size_t)kTiledWarps * 2 * 2 * XR * p.QS * 4;
         const long extent = (long)(h - 1) * sy + (long)(w - 1) * sx + (long)(Q - 1) * sq;      // per-image offsets stay 32-bit in the kernel
         if (groups > kMaxGroups || H > kMaxTableRows || smem > 200 * 1024 || extent >= 2147483647L || sx < 0 || sy < 0 || sq < 0 ||
             p.n_items * ((Q + p.QC - 1) / p.QC) >= 2147483647L) {
-            if (mode == ZUTIS_DECODE_TILED || mode == ZUTIS_DECODE_PRUNED)
+            if (mode == ZUTIS_DECODE_TILED)
                 return fail(ZUTIS_ERR_UNSUPPORTED, "zutis_decode_score: tiled kernel does not fit this shape (groups=%d smem=%zu)", groups, smem);
         } else {
-            // ---- pruned path: champions per low-res pixel, then the pruned kernel on the finite + coherent images and the
-            // tiled kernel on the rest (each kernel returns at once when it has no image)
-            if (use_pruned) {
-                bool launched = false;
-                st = launch_decode_pruned(p, mode == ZUTIS_DECODE_PRUNED, champions_ready, hist_partial ? gt_dtype : ZUTIS_GT_I64,
-                                          workspace, sms, stream, &launched);
-                if (st != ZUTIS_OK) return st;
-            }
             ZUTIS_CUDA(cudaFuncSetAttribute(decode_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int per_sm = 1;
             ZUTIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_tiled_kernel, kTiledWarps * 32, smem));

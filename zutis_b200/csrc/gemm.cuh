@@ -10,9 +10,6 @@ struct GemmParams {
     const float* Bm; long ldb, strideB;
     float* C; long stride_cn, stride_cp, strideC;
     int M; long N; int K; int sigmoid;
-    // optional by-product for the pruned decode kernel (zutis_gemm_logits_champions): per pixel the first-max category,
-    // per image the champion agreements of horizontally adjacent pixels, a non-finite flag and max |logit|
-    int* champ; float* lead; int* img_stats; int img_w;
 };
 
 #ifdef __CUDACC__
@@ -25,6 +22,5 @@ int launch_gemm_simt(const GemmParams& g, int batch, cudaStream_t stream);
 int launch_gemm_tcgen05(const GemmParams& g, int batch, int flags, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t gemm_tcgen05_workspace_bytes(int M, long N, int K, int batch, int flags);
 bool gemm_tcgen05_supports(const GemmParams& g, int batch, int flags);
-bool gemm_tcgen05_makes_champions(const GemmParams& g);
 
 }  // namespace zutis

@@ -105,11 +105,8 @@ static int gemm_logits_impl(const float* A, long lda, long strideA,
                             const float* Bm, long ldb, long strideB,
                             float* C, long stride_cn, long stride_cp, long strideC,
                             int M, long N, int K, int batch, int flags,
-                            void* workspace, size_t workspace_bytes,
-                            int img_w, void* decode_workspace, size_t decode_workspace_bytes, int* champions_written,
-                            void* stream_) {
+                            void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (champions_written) *champions_written = 0;
     ZUTIS_REQUIRE(A && Bm && C, "zutis_gemm_logits: NULL pointer");
     ZUTIS_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "zutis_gemm_logits: non-positive shape M=%d N=%ld K=%d batch=%d", M, N, K, batch);
     ZUTIS_REQUIRE(lda >= K && ldb >= K, "zutis_gemm_logits: row stride smaller than K");
@@ -122,20 +119,12 @@ static int gemm_logits_impl(const float* A, long lda, long strideA,
     g.A = A; g.lda = lda; g.strideA = strideA; g.Bm = Bm; g.ldb = ldb; g.strideB = strideB;
     g.C = C; g.stride_cn = stride_cn; g.stride_cp = stride_cp; g.strideC = strideC;
     g.M = M; g.N = N; g.K = K; g.sigmoid = (flags & ZUTIS_GEMM_SIGMOID) ? 1 : 0;
-    g.champ = nullptr; g.lead = nullptr; g.img_stats = nullptr; g.img_w = 0;
-    if (decode_workspace && img_w > 0 && N % img_w == 0 && decode_workspace_bytes >= decode_ws_bytes(batch, N) &&
-        (reinterpret_cast<uintptr_t>(decode_workspace) & 7) == 0) {
-        g.champ = decode_ws_champ(decode_workspace); g.lead = decode_ws_lead(decode_workspace, batch, N);
-        g.img_stats = decode_ws_stats(decode_workspace, batch, N); g.img_w = img_w;
-    }
     if (prec == ZUTIS_GEMM_FP32_SIMT) return launch_gemm_simt(g, batch, stream);
     if (!gemm_tcgen05_supports(g, batch, flags))
         return fail(ZUTIS_ERR_UNSUPPORTED,
                     "zutis_gemm_logits: tcgen05 path needs K %% 32 == 0, 16-byte aligned K-contiguous rows and M <= 1024 "
                     "(M=%d N=%ld K=%d lda=%ld ldb=%ld); use ZUTIS_GEMM_FP32_SIMT", M, N, K, lda, ldb);
-    st = launch_gemm_tcgen05(g, batch, flags, workspace, workspace_bytes, stream);
-    if (st == ZUTIS_OK && champions_written) *champions_written = gemm_tcgen05_makes_champions(g) ? 1 : 0;
-    return st;
+    return launch_gemm_tcgen05(g, batch, flags, workspace, workspace_bytes, stream);
 }
 
 extern "C" int zutis_gemm_logits(const float* A, long lda, long strideA,
@@ -144,16 +133,5 @@ extern "C" int zutis_gemm_logits(const float* A, long lda, long strideA,
                                  int M, long N, int K, int batch, int flags,
                                  void* workspace, size_t workspace_bytes, void* stream) {
     return gemm_logits_impl(A, lda, strideA, Bm, ldb, strideB, C, stride_cn, stride_cp, strideC, M, N, K, batch, flags,
-                            workspace, workspace_bytes, 0, nullptr, 0, nullptr, stream);
-}
-
-extern "C" int zutis_gemm_logits_champions(const float* A, long lda, long strideA,
-                                           const float* Bm, long ldb, long strideB,
-                                           float* C, long stride_cn, long stride_cp, long strideC,
-                                           int M, long N, int K, int batch, int flags,
-                                           void* workspace, size_t workspace_bytes,
-                                           int img_w, void* decode_workspace, size_t decode_workspace_bytes,
-                                           int* champions_written, void* stream) {
-    return gemm_logits_impl(A, lda, strideA, Bm, ldb, strideB, C, stride_cn, stride_cp, strideC, M, N, K, batch, flags,
-                            workspace, workspace_bytes, img_w, decode_workspace, decode_workspace_bytes, champions_written, stream);
+                            workspace, workspace_bytes, stream);
 }

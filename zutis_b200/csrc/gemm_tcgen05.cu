@@ -69,10 +69,9 @@ struct TcParams {
     int a_col0;       // first TMEM column of the per-stage A operand (64 columns per stage: hi | lo)
     int passes;       // 3 = hi*hi + hi*lo + lo*hi, 1 = hi*hi only
     int sigmoid;
-    int* champ;       // optional: first-max category per pixel, for the pruned decode kernel
-    float* lead;      //           its value minus the largest value of a category with a smaller index
-    int* img_stats;   // optional: [batch] adjacent-champion agreements | [batch] non-finite flags | [batch] bits of max |logit|
-    int img_w;        // low-res image width (pixels per row), for the agreement count
+    // raw fp32 operands, for the exact re-computation of pixels whose products are not finite (epilogue)
+    const float* A; long lda, strideA;
+    const float* Bm; long ldb, strideB;
 };
 
 // ------------------------------------------------------------------------------------ PTX helpers
@@ -370,11 +369,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
             float* crow = p.C + (long)b * p.strideC + pix * p.stride_cp;
             const bool vec_ok = (p.stride_cn == 1) && ((p.stride_cp & 3) == 0) && ((p.strideC & 3) == 0) &&
                                 ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-            // this pixel's champion (p.champ != nullptr: single category tile).  A finite first category always replaces
-            // -inf, so no "unset" state is needed; in an image with a non-finite logit the champions are never used.
-            float ch_best = -INFINITY, ch_prev = -INFINITY;
-            int ch_idx = 0;
-            unsigned ch_abs = 0;                               // max of the magnitude bits: NaN and inf are >= 0x7f800000
+            float row_sum = 0.f;
             for (int c = 0; c < p.umma_n / 16; ++c) {
                 uint32_t v[16];
                 tmem_ld_x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * p.umma_n + c * 16), v);
@@ -382,20 +377,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
                 const int n0 = nt * p.umma_n + c * 16;
                 if (row_ok && n0 < p.M) {
                     float f[16];
+                    const bool whole16 = n0 + 16 <= p.M;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         f[j] = __uint_as_float(v[j]);
+                        if (whole16 || n0 + j < p.M) row_sum = __fadd_rn(row_sum, f[j]);      // NaN / inf anywhere in the row surfaces here
                         if (p.sigmoid) f[j] = sigmoidf_exact(f[j]);
-                    }
-                    if (p.champ) {
-                        const bool whole = n0 + 16 <= p.M;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            if (whole || n0 + j < p.M) {
-                                ch_abs = max(ch_abs, __float_as_uint(f[j]) & 0x7fffffffu);
-                                if (f[j] > ch_best) { ch_prev = ch_best; ch_best = f[j]; ch_idx = n0 + j; }   // prev: best of the categories before it
-                            }
-                        }
                     }
                     if (vec_ok) {
                         // pixel-major rows: padding columns up to the row pitch hold zeros (zero-padded operand rows)
@@ -418,21 +405,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_pix, const __grid_co
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tmem_empty(a));
-            if (p.champ) {
-                if (row_ok) { p.champ[(long)b * p.N + pix] = ch_idx; p.lead[(long)b * p.N + pix] = __fsub_rn(ch_best, ch_prev); }
-                // neighbours inside the warp only (1 pair in 32 is not counted: the count feeds a coarse threshold)
-                const int right = __shfl_down_sync(0xffffffffu, ch_idx, 1);
-                const bool pair = row_ok && lane < 31 && pix + 1 < p.N && ((pix + 1) % p.img_w) != 0 && right == ch_idx;
-                const int agree = __popc(__ballot_sync(0xffffffffu, pair));
-                const bool bad = __any_sync(0xffffffffu, ch_abs >= 0x7f800000u && row_ok);
-                int amax_bits = row_ok ? (int)ch_abs : 0;
-                for (int o = 16; o > 0; o >>= 1) amax_bits = max(amax_bits, __shfl_xor_sync(0xffffffffu, amax_bits, o));
-                if (lane == 0) {
-                    if (agree) atomicAdd(p.img_stats + b, agree);
-                    if (bad) atomicOr(p.img_stats + p.batch + b, 1);
-                    atomicMax(p.img_stats + 2 * p.batch + b, amax_bits);
+            // A non-finite token (or an overflow) cannot go through the hi/lo split: inf - inf = NaN, and inf * 0 in a
+            // correction pass is NaN where fp32 arithmetic keeps the infinity.  Such a pixel -- a whole row of the tile,
+            // since every category multiplies the same token -- is recomputed here from the raw operands as one
+            // ascending-k fmaf chain, which has torch.einsum's NaN / +-inf pattern (zutis.py:361-365).  Rare and slow.
+            if (row_ok && !(fabsf(row_sum) <= 3.402823466e38f)) {
+                const float* trow = p.Bm + (long)b * p.strideB + pix * p.ldb;
+                const int n_end = min(p.M, (nt + 1) * p.umma_n);
+                for (int n = nt * p.umma_n; n < n_end; ++n) {
+                    const float* arow = p.A + (long)b * p.strideA + (long)n * p.lda;
+                    float acc = 0.f;
+                    for (int k = 0; k < p.K; ++k) acc = __fmaf_rn(__ldg(arow + k), __ldg(trow + k), acc);
+                    crow[(long)n * p.stride_cn] = p.sigmoid ? sigmoidf_exact(acc) : acc;
                 }
             }
+            __syncwarp();
         }
     } else if (warp >= 8) {
         // =============================== converters ===============================
@@ -566,10 +553,6 @@ size_t gemm_tcgen05_workspace_bytes(int M, long, int K, int batch, int) {
     return (size_t)2 * batch * pl.rows_per_image * K * 4;
 }
 
-bool gemm_tcgen05_makes_champions(const GemmParams& g) {
-    return g.champ && g.lead && g.img_stats && g.img_w > 0 && make_plan(g.M).n_tiles == 1 && !g.sigmoid;
-}
-
 bool gemm_tcgen05_supports(const GemmParams& g, int batch, int flags) {
     if ((flags & ZUTIS_GEMM_PRECISION_MASK) == ZUTIS_GEMM_FP32_SIMT) return false;
     if (g.K % BLOCK_K != 0 || g.M > 1024) return false;
@@ -619,11 +602,8 @@ int launch_gemm_tcgen05(const GemmParams& g, int batch, int flags, void* workspa
     p.sa = pl.sa; p.sb = pl.sb; p.st = pl.st; p.b_slot_bytes = pl.b_slot_bytes; p.tmem_cols = pl.tmem_cols; p.acc_bufs = pl.acc_bufs; p.a_col0 = pl.a_col0;
     p.passes = ((flags & ZUTIS_GEMM_PRECISION_MASK) == ZUTIS_GEMM_TF32X3) ? 3 : 1;
     p.sigmoid = g.sigmoid;
-    // the champion by-product needs every category of a pixel in one thread: single category tile, raw logits
-    const bool champs = g.champ && g.lead && g.img_stats && g.img_w > 0 && pl.n_tiles == 1 && !g.sigmoid;
-    p.champ = champs ? g.champ : nullptr; p.lead = champs ? g.lead : nullptr; p.img_stats = champs ? g.img_stats : nullptr; p.img_w = g.img_w;
+    p.A = g.A; p.lda = g.lda; p.strideA = g.strideA; p.Bm = g.Bm; p.ldb = g.ldb; p.strideB = g.strideB;
 
-    if (champs) ZUTIS_CUDA(cudaMemsetAsync(g.img_stats, 0, decode_ws_counter_bytes(batch), stream));
     const size_t smem = pl.smem;
     ZUTIS_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long total_tiles = (long)batch * p.p_tiles * p.n_tiles;

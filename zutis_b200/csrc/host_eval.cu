@@ -30,7 +30,7 @@ struct Lane {
     float* logits = nullptr;
     int16_t* labels = nullptr;
     int32_t* partial = nullptr;
-    void* decode_ws = nullptr;       // champions of the pruning decode kernel, filled by the contraction's epilogue
+    void* decode_ws = nullptr;       // run counter of the cell decode kernel
 };
 
 }  // namespace
@@ -99,14 +99,11 @@ extern "C" int zutis_semantic_eval_host(const float* text, const float* tokens, 
         if (gt && rc == ZUTIS_OK)
             guard(check_cuda(cudaMemcpyAsync(L.gt, (const char*)gt + (size_t)b0 * HW * gt_bytes, (size_t)nb * HW * gt_bytes, cudaMemcpyHostToDevice, L.stream), "H2D gt"));
         if (rc != ZUTIS_OK) break;
-        int champions = 0;
-        guard(zutis_gemm_logits_champions(d_text, D, 0, L.tokens, D, hw * D, L.logits, 1, Qp, hw * Qp, Q, hw, D, nb, gemm_flags,
-                                          d_ws ? (char*)d_ws + ws_bytes * (it % nlanes) : nullptr, ws_bytes,
-                                          w, L.decode_ws, dws_bytes, &champions, L.stream));
+        guard(zutis_gemm_logits(d_text, D, 0, L.tokens, D, hw * D, L.logits, 1, Qp, hw * Qp, Q, hw, D, nb, gemm_flags,
+                                d_ws ? (char*)d_ws + ws_bytes * (it % nlanes) : nullptr, ws_bytes, L.stream));
         if (rc != ZUTIS_OK) break;
         guard(zutis_decode_score_ws(L.logits, hw * Qp, 1, (long)w * Qp, Qp, nb, Q, h, w, H, W, L.gt, gt_dtype, HW,
-                                    L.labels, hist_host ? L.partial : nullptr, Q,
-                                    ZUTIS_DECODE_AUTO | (champions ? ZUTIS_DECODE_CHAMPIONS_READY : 0), L.decode_ws, dws_bytes, L.stream));
+                                    L.labels, hist_host ? L.partial : nullptr, Q, ZUTIS_DECODE_AUTO, L.decode_ws, dws_bytes, L.stream));
         if (labels_host && rc == ZUTIS_OK)
             guard(check_cuda(cudaMemcpyAsync(labels_host + (size_t)b0 * HW, L.labels, (size_t)nb * HW * 2, cudaMemcpyDeviceToHost, L.stream), "D2H labels"));
     }

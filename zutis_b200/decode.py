@@ -148,10 +148,9 @@ def predict(
     text = self.text_embeddings
     if mask_type == "semantic":
         tokens = dict_outputs["patch_tokens"]                      # b x h x w x n_dims
-        ws = self.__dict__.setdefault("_zutis_b200_decode_ws", ops.DecodeWorkspace())   # champions for the pruning decode kernel
+        ws = self.__dict__.setdefault("_zutis_b200_decode_ws", ops.DecodeWorkspace())   # run counter of the cell decode kernel
         lowres = ops.contraction(text.to(tokens.device), tokens, precision=precision,
-                                 a_cache=self.__dict__.setdefault("_zutis_b200_text_cache", {}),
-                                 decode_ws=None if return_logits else ws)                              # b x n x h x w
+                                 a_cache=self.__dict__.setdefault("_zutis_b200_text_cache", {}))       # b x n x h x w
         if return_logits:
             # the one mode in which full-resolution logits are materialised, on request (zutis.py:369-370)
             return ops.upsample_bilinear(lowres, size) if size is not None else lowres
@@ -260,10 +259,9 @@ def decode_and_score(text: torch.Tensor, patch_tokens: torch.Tensor, label_trues
     Equivalent to ``meter.update(label_trues, predict(..., "semantic", size=size))``
     (trainer.py:331-347) without materialising logits or labels on the host.
     """
-    # the contraction's epilogue also leaves the per-pixel champions the pruning decode kernel needs in `ws`
     ws = meter.__dict__.setdefault("_decode_ws", ops.DecodeWorkspace())
     cache = meter.__dict__.setdefault("_text_cache", {})
-    lowres = ops.contraction(text, patch_tokens, precision=precision, a_cache=cache, decode_ws=ws)
+    lowres = ops.contraction(text, patch_tokens, precision=precision, a_cache=cache)
     return meter.update_from_logits(lowres, label_trues, size=size, want_labels=want_labels, workspace=ws)
 
 

@@ -9,7 +9,6 @@ from __future__ import annotations
 from typing import Optional, Tuple
 
 import ctypes as C
-import weakref
 
 import numpy as np
 import torch
@@ -62,37 +61,27 @@ def gemm_flags(precision: Optional[str], sigmoid: bool = False) -> int:
 
 
 class DecodeWorkspace:
-    """Device scratch of the candidate-pruning decode kernel (champion per low-res pixel, per-image counters).
+    """The 16 bytes of device scratch behind ``zutis_decode_score_ws``: the cell decode kernel's global run counter.
 
-    Pass the same object to ``contraction(..., decode_ws=ws)`` and ``decode_score(..., workspace=ws)``: the tensor-core
-    contraction then fills it in its epilogue and the decode call skips its own champion pass."""
+    One buffer per (device, stream), since two launches that overlap must not share a counter.  A buffer is zero-filled
+    when it is created and every launch leaves it zero, so calls through it enqueue no memset."""
 
     def __init__(self):
-        self.buf: Optional[torch.Tensor] = None
-        # (weakref to the logits buffer, shape, version) the champions in ``buf`` belong to.  A weak reference, not a
-        # data pointer: the caching allocator hands a freed address (with version 0) to the next tensor of that size.
-        self.ready_for: Optional[tuple] = None
+        self.bufs: dict = {}
 
     def ensure(self, nbytes: int, device) -> torch.Tensor:
-        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
-            self.buf = torch.empty(max(nbytes, 8), device=device, dtype=torch.uint8)
-            self.ready_for = None
-        return self.buf
+        key = (str(device), _stream())
+        buf = self.bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = self.bufs[key] = torch.zeros(max(nbytes, 16), device=device, dtype=torch.uint8)
+        return buf
 
-    def mark_ready(self, logits_buf: torch.Tensor, shape: tuple) -> None:
-        self.ready_for = (weakref.ref(logits_buf), tuple(shape), logits_buf._version)
 
-    def holds_champions_of(self, logits: torch.Tensor) -> bool:
-        if self.ready_for is None:
-            return False
-        ref, shape, version = self.ready_for
-        base = logits._base if logits._base is not None else logits
-        return ref() is base and tuple(logits.shape) == shape and logits._version == version
+_default_workspace = None           # for callers that do not bring one
 
 
 def contraction(a: torch.Tensor, feats: torch.Tensor, *, precision: Optional[str] = None, sigmoid: bool = False,
-                pixel_major: bool = True, a_cache: Optional[dict] = None,
-                decode_ws: Optional[DecodeWorkspace] = None) -> torch.Tensor:
+                pixel_major: bool = True, a_cache: Optional[dict] = None) -> torch.Tensor:
     """out[b,n,y,x] = act(sum_c a[(b,)n,c] * feats[b,y,x,c])   (zutis.py:361-365, :184-186 + :209).
 
     a: [M,C] shared by the batch (text embeddings) or [B,M,C] per image (queries).
@@ -151,23 +140,10 @@ def contraction(a: torch.Tensor, feats: torch.Tensor, *, precision: Optional[str
         elif ws_bytes:
             ws = torch.empty(ws_bytes, device=feats.device, dtype=torch.uint8)
         with torch.cuda.device(feats.device):
-            if decode_ws is not None and pixel_major and not sigmoid:
-                dws_bytes = F.lib().zutis_decode_workspace_bytes(B, M, h, w, h, w)
-                dws = decode_ws.ensure(dws_bytes, feats.device)
-                written = C.c_int(0)
-                decode_ws.ready_for = None
-                F.call("zutis_gemm_logits_champions", a.data_ptr(), a.stride(-2), 0 if shared else a.stride(0),
-                       feats.data_ptr(), feats.stride(2), feats.stride(0),
-                       buf.data_ptr(), s_cn, s_cp, s_c, M, N, Cc, B, fl,
-                       ws.data_ptr() if ws is not None else None, ws_bytes,
-                       w, dws.data_ptr(), dws_bytes, C.addressof(written), _stream())
-                if written.value:
-                    decode_ws.mark_ready(buf, (B, M, h, w))      # an in-place change of the logits invalidates the champions
-            else:
-                F.call("zutis_gemm_logits", a.data_ptr(), a.stride(-2), 0 if shared else a.stride(0),
-                       feats.data_ptr(), feats.stride(2), feats.stride(0),
-                       buf.data_ptr(), s_cn, s_cp, s_c, M, N, Cc, B, fl,
-                       ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
+            F.call("zutis_gemm_logits", a.data_ptr(), a.stride(-2), 0 if shared else a.stride(0),
+                   feats.data_ptr(), feats.stride(2), feats.stride(0),
+                   buf.data_ptr(), s_cn, s_cp, s_c, M, N, Cc, B, fl,
+                   ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
         if cache_key is not None and not (fl & F.GEMM_A_PREPARED):
             a_cache["entry"] = (a, a._version, cache_key, ws)    # only once the launch that prepared it has succeeded
 
@@ -213,16 +189,15 @@ def decode_score(logits: torch.Tensor, size=None, *, gt: Optional[torch.Tensor] 
         if hist_partial.dtype != torch.int32 or hist_partial.numel() != n_classes * n_classes or not hist_partial.is_contiguous():
             raise ValueError("hist_partial must be a contiguous int32 tensor with n_classes^2 elements")
     with torch.cuda.device(logits.device):
-        # scratch for the candidate-pruning kernel (champion per low-res pixel); the library ignores it when the
-        # shape or the strides rule that kernel out
+        # the cell kernel's run counter (dynamic work distribution); the library ignores it when another kernel runs
         ws_bytes = F.lib().zutis_decode_workspace_bytes(B, Q, h, w, H, W)
-        if workspace is not None:
-            ws = workspace.ensure(ws_bytes, logits.device)
-            if workspace.holds_champions_of(logits):
-                mode |= F.DECODE_CHAMPIONS_READY             # the contraction's epilogue already filled it for these logits
-            workspace.ready_for = None
-        else:
-            ws = torch.empty(max(ws_bytes, 8), device=logits.device, dtype=torch.uint8)
+        if workspace is None:
+            global _default_workspace
+            if _default_workspace is None:
+                _default_workspace = DecodeWorkspace()
+            workspace = _default_workspace
+        ws = workspace.ensure(ws_bytes, logits.device)
+        mode |= F.DECODE_WORKSPACE_ZEROED                    # created zero-filled, left zero by every launch
         F.call("zutis_decode_score_ws", logits.data_ptr(), logits.stride(0), logits.stride(1), logits.stride(2), logits.stride(3),
                B, Q, h, w, H, W, gt_ptr, gt_code, gt_sb,
                labels.data_ptr() if labels is not None else None,

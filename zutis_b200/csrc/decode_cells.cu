@@ -44,7 +44,7 @@ constexpr int kRunCells = 4;       // cells per run = 32 lanes / 8 slices
 constexpr int kSlices = 8;
 constexpr int kBoxPixels = kRunCells + 1;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kCellWarpsMax = 24;   // 768 threads: 85 registers per thread (at 64 the kernel spills and re-derives its addresses)
+constexpr int kCellWarpsMax = 20;   // 640 threads: 96 registers per thread, no spills (80 registers spill; the spills go to L2 because shared memory leaves no L1)
 
 // Make a value opaque to the optimiser: it stays in its register instead of being re-derived from kernel parameters
 // and special registers at every use (the compiler otherwise rematerialises shared-memory base addresses all over).
@@ -165,7 +165,7 @@ struct CellParams {
     int pair_ok;             // W even, labels 4-byte aligned, ground truth aligned for pair loads
     int tap_pitch_bytes;     // staged taps: bytes between low-res pixels of the box (= 4 * ceil4(Q))
     int tap_bytes;           // bytes of one staged box (2 rows x 5 pixels), rounded up to 128
-    int off_ystart, off_xstart, off_ly, off_lx, off_warp, warp_bytes;    // byte offsets in dynamic shared memory
+    int off_ystart, off_xstart, off_ly, off_lx, off_lyp, off_warp, warp_bytes;    // byte offsets in dynamic shared memory
 };
 
 // NI: float4 iterations per lane in phase P (ceil(ceil(Q/4) / 8)), taps staged in shared memory by TMA;
@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(kCellWarpsMax * 32, 1) decode_cells_kernel(con
 #define a_xstart (a_hist + (uint32_t)p.off_xstart)                              /* [w+1] */
 #define a_ly (a_hist + (uint32_t)p.off_ly)                                      /* [H] float2 (ly0, ly1) */
 #define a_lx (a_hist + (uint32_t)p.off_lx)                                      /* [W] float4 (lx0, lx0, lx1, lx1): packed operands */
+#define a_lyp (a_hist + (uint32_t)p.off_lyp)                                    /* [H] float4 (ly0[Y], ly0[Y+1], ly1[Y], ly1[Y+1]) */
     // warp-private: [staged taps: 2 rows x 5 pixels x Qp] [survivors' corner values (A, C, B, D): kRunCells x (cap+1) float4]
     //               [their categories: kRunCells x (cap+1) u16] [mbarrier]
     const int cap = p.cap;
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(kCellWarpsMax * 32, 1) decode_cells_kernel(con
 #define val_base (tap_base + (STAGED ? (uint32_t)p.tap_bytes : 0u))
 #define id_base (val_base + (uint32_t)(kRunCells * (cap + 1) * 16))
 #define bar (tap_base + (uint32_t)p.warp_bytes - 8u)
+#define sent_addr (tap_base + (uint32_t)p.warp_bytes - 32u)                     /* one survivor record of -inf: never a strict maximum */
     // only the two roots are pinned; everything else is root + kernel parameter (one IADD with a constant-bank operand)
     ZUTIS_KEEP(a_hist); ZUTIS_KEEP(tap_base);
 
@@ -206,6 +208,12 @@ __global__ void __launch_bounds__(kCellWarpsMax * 32, 1) decode_cells_kernel(con
         for (int c = threadIdx.x; c <= p.w; c += blockDim.x) xstart[c] = first_dst_with_tap_ge(c, p.w, p.W, p.scale_x);
         for (int Y = threadIdx.x; Y < p.H; Y += blockDim.x) { const AxisTap t = axis_tap(Y, p.h, p.H, p.scale_y); ly[Y] = make_float2(t.l0, t.l1); }
         for (int X = threadIdx.x; X < p.W; X += blockDim.x) { const AxisTap t = axis_tap(X, p.w, p.W, p.scale_x); lx[X] = make_float4(t.l0, t.l0, t.l1, t.l1); }
+        float4* lyp = reinterpret_cast<float4*>(smem_c + p.off_lyp);
+        for (int Y = threadIdx.x; Y < p.H; Y += blockDim.x) {
+            const AxisTap t0 = axis_tap(Y, p.h, p.H, p.scale_y), t1 = axis_tap(min(Y + 1, p.H - 1), p.h, p.H, p.scale_y);
+            lyp[Y] = make_float4(t0.l0, t1.l0, t0.l1, t1.l1);
+        }
+        if (lane == 0) sts128(sent_addr, -INFINITY, -INFINITY, -INFINITY, -INFINITY);
         if (threadIdx.x == 0) { s_next = 0; if (STAGED) tma_prefetch_descriptor(&tap_map); }
         if (STAGED && lane == 0) { mbarrier_init(bar, 1); fence_mbarrier_init(); }
     }
@@ -224,11 +232,16 @@ __global__ void __launch_bounds__(kCellWarpsMax * 32, 1) decode_cells_kernel(con
     // of warps): 7000 warps asking one address at once would start the kernel with several microseconds of queueing.
     const unsigned n_warps_grid = gridDim.x * (blockDim.x >> 5);
     unsigned static_next = blockIdx.x * (blockDim.x >> 5) + (unsigned)warp;
+    // (inline PTX: with atomicAdd the compiler aggregates over the warp and reads the result at once, which would put the
+    // atomic's round trip right here instead of two phases later, where the value is first needed)
     auto request = [&]() -> unsigned {
         unsigned g = 0;
         if (p.counter) {
             if (static_next < 2u * n_warps_grid) { g = static_next; static_next += n_warps_grid; }
-            else if (lane == 0) g = atomicAdd(p.counter, 1u) + 2u * n_warps_grid;
+            else if (lane == 0) {
+                asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(g) : "l"(p.counter) : "memory");
+                g += 2u * n_warps_grid;
+            }
         } else if (lane == 0) g = atomicAdd(&s_next, 1u);
         return g;
     };
@@ -397,8 +410,7 @@ __global__ void __launch_bounds__(kCellWarpsMax * 32, 1) decode_cells_kernel(con
             if (!(fabsf(tot) <= 3.402823466e38f)) n = cap + 1;
         }
         __syncwarp();
-        // ---- gather, lane = list entry of the run: survivor j of cell c -> (A, C, B, D) next to its index.  Lists of odd
-        // length get a sentinel (-inf everywhere: never a strict maximum) so that the evaluation walks them in pairs.
+        // ---- gather, lane = list entry of the run: survivor j of cell c -> (A, C, B, D) next to its index
         const int cells_here = min(kRunCells, p.w - cx_begin);
         const int n0 = __shfl_sync(kFull, n, 0), n1 = __shfl_sync(kFull, n, 8), n2 = __shfl_sync(kFull, n, 16), n3 = __shfl_sync(kFull, n, 24);
         {
@@ -406,7 +418,7 @@ __global__ void __launch_bounds__(kCellWarpsMax * 32, 1) decode_cells_kernel(con
             const int e1 = (n1 >= 2 && n1 <= cap && cells_here > 1) ? n1 : 0;
             const int e2 = (n2 >= 2 && n2 <= cap && cells_here > 2) ? n2 : 0;
             const int e3 = (n3 >= 2 && n3 <= cap && cells_here > 3) ? n3 : 0;
-            const int f0 = e0 + (e0 & 1), f01 = f0 + e1 + (e1 & 1), f012 = f01 + e2 + (e2 & 1), total = f012 + e3 + (e3 & 1);
+            const int f0 = e0, f01 = f0 + e1, f012 = f01 + e2, total = f012 + e3;
             for (int e = lane; e < total; e += 32) {
                 const int c = (e >= f0) + (e >= f01) + (e >= f012);
                 const int j = e - (c == 0 ? 0 : (c == 1 ? f0 : (c == 2 ? f01 : f012)));
@@ -451,81 +463,96 @@ __global__ void __launch_bounds__(kCellWarpsMax * 32, 1) decode_cells_kernel(con
             }
         }
 
-        // ------------------------------------------------------------------ E: evaluate (lane = pixel pair of an 8x8 tile)
+        // ------------------------------------------------------------------ E: evaluate
         const int ys = (int)lds_u32(a_ystart + (uint32_t)cy * 4u), ye = (int)lds_u32(a_ystart + (uint32_t)cy * 4u + 4u);
         const unsigned img_px = (unsigned)b * (unsigned)(p.H * p.W);
         const GT* gt_img = gt_base + (size_t)b * p.gt_sb;
-        const bool full_rows = (ye - ys == 8);
-        // fast path: this lane's pixel pair (row ys + r8, columns xs + c2, +1), the cell's first column xs still missing
-        const unsigned lane_px = (unsigned)(ys + r8) * (unsigned)p.W + (unsigned)c2;
-        const GT* gt_lane = gt_img + lane_px;
-        int16_t* lbl_lane = p.labels ? p.labels + (img_px + lane_px) : nullptr;
-        const float2 ly_fast = lds_f2(a_ly + (uint32_t)min(ys + r8, p.H - 1) * 8u);
-        // ground truth one cell ahead (its DRAM / L2 latency hides behind the previous cell's evaluation)
-        int xs_next = (int)lds_u32(a_xstart + (uint32_t)cx_begin * 4u);
-        typename Pair<GT>::type gt_ahead = typename Pair<GT>::type();
-        if (p.hist && p.pair_ok && full_rows && (xs_next & 1) == 0) gt_ahead = *reinterpret_cast<const typename Pair<GT>::type*>(gt_lane + xs_next);
+        // ---- all full 8x8 cells of the run at once: lane = (cell, column), 8 rows per lane.  The four lists are walked
+        // together (a lane past the end of its list reads the -inf record), so the per-run work is shared by the cells.
+        unsigned fast_mask;
+        {
+            const int xs_m = (int)lds_u32(a_xstart + (uint32_t)min(cx_begin + cell, p.w) * 4u);
+            const int xe_m = (int)lds_u32(a_xstart + (uint32_t)min(cx_begin + cell + 1, p.w) * 4u);
+            const bool fast_m = (ye - ys == 8) && cell < cells_here && (xe_m - xs_m == 8) && n <= cap;
+            fast_mask = __ballot_sync(kFull, fast_m);
+            if (fast_mask) {
+                const int X = min(xs_m + slice, p.W - 1);
+                const unsigned px0 = (unsigned)ys * (unsigned)p.W + (unsigned)X;                 // row ys of this lane's column
+                GT g[8];
+                if (p.hist) {
+                    const GT* gp = gt_img + px0;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) g[r] = fast_m ? gp[(size_t)r * p.W] : (GT)-1;
+                }
+                const int nloop = (fast_m && n >= 2) ? n : 0;
+                const int maxn = __reduce_max_sync(kFull, nloop);
+                const float4 lx = lds128(a_lx + (uint32_t)X * 16u);
+                const unsigned long long LX0 = pack2(lx.x, lx.y), LX1 = pack2(lx.z, lx.w);
+                unsigned long long LY0[4], LY1[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 t = lds128(a_lyp + (uint32_t)(ys + 2 * q) * 16u);
+                    LY0[q] = pack2(t.x, t.y); LY1[q] = pack2(t.z, t.w);
+                }
+                float best[8];
+                int win[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) { best[r] = -INFINITY; win[r] = 0; }
+                const uint32_t val_m = val_base + (uint32_t)(cell * (cap + 1)) * 16u;
+#pragma unroll 1
+                for (int j = 0; j < maxn; ++j) {
+                    const float4 v = lds128(j < nloop ? val_m + (uint32_t)j * 16u : sent_addr);
+                    float t, u;
+                    unpack2(fma2(LX0, pack2(v.x, v.y), mul2(LX1, pack2(v.z, v.w))), t, u);      // t = fma(lx0,A,lx1*B), u = fma(lx0,C,lx1*D)
+                    const unsigned long long tt = pack2(t, t), uu = pack2(u, u);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float v0, v1;
+                        unpack2(fma2(LY0[q], tt, mul2(LY1[q], uu)), v0, v1);                    // rows 2q, 2q+1: fma(ly0, t, ly1*u)
+                        if (v0 > best[2 * q]) { best[2 * q] = v0; win[2 * q] = j; }
+                        if (v1 > best[2 * q + 1]) { best[2 * q + 1] = v1; win[2 * q + 1] = j; }
+                    }
+                }
+                const uint32_t ids_m = id_base + (uint32_t)(cell * (cap + 1)) * 2u;
+                int lab[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) lab[r] = (int)lds_u16(ids_m + (uint32_t)win[r] * 2u);
+                if (p.labels && fast_m) {
+                    int16_t* out = p.labels + (img_px + px0);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) out[(size_t)r * p.W] = (int16_t)lab[r];
+                }
+                if (p.hist) {
+#pragma unroll
+                    for (int r = 0; r < 8; r += 2) {
+                        const int key0 = (fast_m && label_in_range<GT>(g[r], p.n)) ? (int)g[r] * p.n + lab[r] : -1;
+                        const int key1 = (fast_m && label_in_range<GT>(g[r + 1], p.n)) ? (int)g[r + 1] * p.n + lab[r + 1] : -1;
+                        // lanes with the same (key0, key1) elect one leader
+                        const unsigned peers = __match_any_sync(kFull, ((unsigned long long)(unsigned)key0 << 32) | (unsigned)key1);
+                        if (lane == __ffs(peers) - 1) {
+                            const int c = __popc(peers);
+                            if (p.hist_in_smem) {
+                                if (key0 == key1) { if (key0 >= 0) red_shared_add(a_hist + (uint32_t)key0 * 4u, 2 * c); }
+                                else { if (key0 >= 0) red_shared_add(a_hist + (uint32_t)key0 * 4u, c); if (key1 >= 0) red_shared_add(a_hist + (uint32_t)key1 * 4u, c); }
+                            } else {
+                                if (key0 == key1) { if (key0 >= 0) atomicAdd(p.hist + key0, 2 * c); }
+                                else { if (key0 >= 0) atomicAdd(p.hist + key0, c); if (key1 >= 0) atomicAdd(p.hist + key1, c); }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // ---- the other cells of the run, one at a time: lane = pixel pair of an 8x8 tile of the cell
 #pragma unroll 1
         for (int ci = 0; ci < cells_here; ++ci) {
+            if (fast_mask & (1u << (ci * kSlices))) continue;
             const int cx = cx_begin + ci;
             const int nc = __shfl_sync(kFull, n, ci * kSlices);
-            const int xs = xs_next, xe = (int)lds_u32(a_xstart + (uint32_t)cx * 4u + 4u);
-            xs_next = xe;
+            const int xs = (int)lds_u32(a_xstart + (uint32_t)cx * 4u), xe = (int)lds_u32(a_xstart + (uint32_t)cx * 4u + 4u);
             const uint32_t val = val_base + (uint32_t)(ci * (cap + 1)) * 16u;
             const uint32_t ids = id_base + (uint32_t)(ci * (cap + 1)) * 2u;
             const bool vec = p.pair_ok && ((xs & 1) == 0);
-            const typename Pair<GT>::type gt_now = gt_ahead;
-            // (a pair that straddles the end of the image row is never read: the next cell is then a border cell or absent)
-            if (p.hist && p.pair_ok && full_rows && (xe & 1) == 0 && ci + 1 < cells_here && xe + 8 <= p.W)
-                gt_ahead = *reinterpret_cast<const typename Pair<GT>::type*>(gt_lane + xe);
-            if (vec && full_rows && xe - xs == 8 && nc <= cap) {
-                // ---- the common case.  No bounds, no tile loop.
-                unsigned i0, i1;
-                if (nc == 1) {
-                    i0 = i1 = lds_u16(ids);
-                } else {
-                    const uint32_t lxa = a_lx + (uint32_t)(xs + c2) * 16u;
-                    const float4 la = lds128(lxa), lb = lds128(lxa + 16u);
-                    const unsigned long long LA0 = pack2(la.x, la.y), LA1 = pack2(la.z, la.w);
-                    const unsigned long long LB0 = pack2(lb.x, lb.y), LB1 = pack2(lb.z, lb.w);
-                    float best0 = -INFINITY, best1 = -INFINITY;
-                    const uint32_t last = val + (uint32_t)nc * 16u;
-                    uint32_t w0 = val, w1 = val;
-                    for (uint32_t at = val; at < last; at += 32u) {                      // two entries per trip (sentinel-padded)
-#pragma unroll
-                        for (uint32_t h2 = 0; h2 < 32u; h2 += 16u) {
-                            const float4 v = lds128(at + h2);
-                            const unsigned long long ac = pack2(v.x, v.y), bd = pack2(v.z, v.w);
-                            float t0, u0, t1, u1;
-                            unpack2(fma2(LA0, ac, mul2(LA1, bd)), t0, u0);      // t = fma(lx0,A,lx1*B), u = fma(lx0,C,lx1*D)
-                            unpack2(fma2(LB0, ac, mul2(LB1, bd)), t1, u1);
-                            const float v0 = __fmaf_rn(ly_fast.x, t0, __fmul_rn(ly_fast.y, u0));
-                            const float v1 = __fmaf_rn(ly_fast.x, t1, __fmul_rn(ly_fast.y, u1));
-                            if (v0 > best0) { best0 = v0; w0 = at + h2; }
-                            if (v1 > best1) { best1 = v1; w1 = at + h2; }
-                        }
-                    }
-                    i0 = lds_u16(ids + ((w0 - val) >> 3)); i1 = lds_u16(ids + ((w1 - val) >> 3));
-                }
-                if (lbl_lane) *reinterpret_cast<uint32_t*>(lbl_lane + xs) = i0 | (i1 << 16);
-                if (p.hist) {
-                    const GT g0 = (GT)gt_now.x, g1 = (GT)gt_now.y;
-                    const int key0 = label_in_range<GT>(g0, p.n) ? (int)g0 * p.n + (int)i0 : -1;
-                    const int key1 = label_in_range<GT>(g1, p.n) ? (int)g1 * p.n + (int)i1 : -1;
-                    const unsigned peers = __match_any_sync(kFull, ((unsigned long long)(unsigned)key0 << 32) | (unsigned)key1);
-                    if (lane == __ffs(peers) - 1) {
-                        const int c = __popc(peers);
-                        if (p.hist_in_smem) {
-                            if (key0 == key1) { if (key0 >= 0) red_shared_add(a_hist + (uint32_t)key0 * 4u, 2 * c); }
-                            else { if (key0 >= 0) red_shared_add(a_hist + (uint32_t)key0 * 4u, c); if (key1 >= 0) red_shared_add(a_hist + (uint32_t)key1 * 4u, c); }
-                        } else {
-                            if (key0 == key1) { if (key0 >= 0) atomicAdd(p.hist + key0, 2 * c); }
-                            else { if (key0 >= 0) atomicAdd(p.hist + key0, c); if (key1 >= 0) atomicAdd(p.hist + key1, c); }
-                        }
-                    }
-                }
-                continue;
-            }
             // ---- general case: any cell shape, odd alignment, list overflow, non-finite taps
             for (int ty = ys; ty < ye; ty += 8) {
                 const int Y = ty + r8;
@@ -629,6 +656,8 @@ __global__ void __launch_bounds__(kCellWarpsMax * 32, 1) decode_cells_kernel(con
 #undef a_xstart
 #undef a_ly
 #undef a_lx
+#undef a_lyp
+#undef sent_addr
 #undef val_base
 #undef id_base
 #undef bar
@@ -680,12 +709,13 @@ int launch_decode_cells(const DecodeParams& d, bool forced, int label_dtype, uns
     if (p.cap > Qp) p.cap = Qp;
     p.tap_pitch_bytes = Qp * 4;
     p.tap_bytes = staged ? ((2 * kBoxPixels * p.tap_pitch_bytes + 127) & ~127) : 0;
-    p.warp_bytes = (p.tap_bytes + kRunCells * (p.cap + 1) * 18 + 8 + 127) & ~127;
+    p.warp_bytes = (p.tap_bytes + kRunCells * (p.cap + 1) * 18 + 32 + 127) & ~127;       // + the -inf record and the barrier
     p.off_ystart = (p.hist_in_smem ? ((nn + 3) & ~3) : 0) * 4;
     p.off_xstart = p.off_ystart + ((d.h + 1 + 3) & ~3) * 4;
     p.off_ly = p.off_xstart + ((d.w + 1 + 3) & ~3) * 4;
     p.off_lx = p.off_ly + ((d.H + 1) & ~1) * 8;             // 16-byte aligned: float4 per output column
-    p.off_warp = (p.off_lx + d.W * 16 + 127) & ~127;
+    p.off_lyp = p.off_lx + d.W * 16;
+    p.off_warp = (p.off_lyp + d.H * 16 + 127) & ~127;
     const size_t smem_max = 226 * 1024;
     size_t smem = (size_t)p.off_warp + (size_t)warps * p.warp_bytes;
     while (smem > smem_max && warps > 8) { warps -= 2; smem = (size_t)p.off_warp + (size_t)warps * p.warp_bytes; }

@@ -800,6 +800,7 @@ def main():
         run_reference(args, cfg, rank, world)
         return
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")        # NCCL's version banner goes to stdout; the contract is ONE JSON line
         from zutis_b200.distributed import init_distributed
         init_distributed("nccl")
     try:

@@ -197,6 +197,16 @@ ZUTIS_API int zutis_instance_lowres_stats(const float* probs, long sb, long sq, 
                                           float threshold, int32_t* sizes, float* psum, float* mean_tokens,
                                           void* stream);
 
+/* The same statistics with the masked average computed as a [Q, hw] x [hw, D] contraction per image on the tensor cores
+ * (0/1 mask operand, tokens through the 3xTF32 split: fp32-grade sums) instead of the reference's [B,Q,h,w,D] broadcast.
+ * workspace: >= zutis_instance_stats_workspace_bytes, 256-byte aligned; NULL / too small / a shape the contraction
+ * kernel does not take runs zutis_instance_lowres_stats's kernel instead (same results up to summation order). */
+ZUTIS_API size_t zutis_instance_stats_workspace_bytes(int B, int Q, int h, int w, int D);
+ZUTIS_API int zutis_instance_lowres_stats_ws(const float* probs, long sb, long sq, long sy, long sx,
+                                             const float* tokens, int B, int Q, int h, int w, int D,
+                                             float threshold, int32_t* sizes, float* psum, float* mean_tokens,
+                                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* Category decision per query                                      networks/zutis.py:409-420
  * mean_tokens [n_rows,D] (n_rows = B*Q), text [n_categories,D] unit rows:
  * prob[n] = sigmoid(temperature * <text[n], t/(|t|+1e-7)>); category = first argmax, max_prob = max. */

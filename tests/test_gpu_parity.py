@@ -699,3 +699,68 @@ def test_image_to_text_space_drop_in(zb, golden):
     ref = O.torch_image_to_text_space(tok[:2].cpu(), proj.cpu())
     np.testing.assert_allclose(got[:2].cpu().numpy(), ref.numpy(), rtol=0, atol=3e-6)
     assert float((got.norm(dim=-1) - 1).abs().max()) < 1e-5
+
+
+def test_polling_scores_every_batch_does_not_serialise_the_stream(zb):
+    """trainer.py:178 / :348 read the scores after EVERY batch.  With get_scores_async + poll_scores the host never waits:
+    after enqueueing all batches the stream must still be busy, the polled scores are those of an earlier batch (or
+    None), and once everything has landed they equal the blocking get_scores() bit for bit."""
+    import time
+    gen = torch.Generator().manual_seed(2)
+    B, Q, D, h, w, H, W = 32, 81, 512, 40, 40, 320, 320
+    text = torch.nn.functional.normalize(torch.randn(Q, D, generator=gen), dim=-1).cuda()
+    coarse = torch.randn(B, D, h // 2, w // 2, generator=gen)
+    tokens = torch.nn.functional.normalize(torch.nn.functional.interpolate(coarse, scale_factor=2, mode="bilinear").permute(0, 2, 3, 1), dim=-1).contiguous().cuda()
+    gt = torch.randint(0, Q, (B, H, W), generator=gen).cuda()
+    meter = zb.RunningScore(Q)
+    zb.decode_and_score(text, tokens, gt, (H, W), meter)           # warm-up: workspace, prepared operand, pinned buffer
+    meter.get_scores_async(); torch.cuda.synchronize(); assert meter.poll_scores() is not None
+    meter.reset()
+    assert meter.poll_scores() is None
+    n_batches, seen = 40, []
+    torch.cuda.synchronize()
+    # keep the device busy for ~60 ms first: every call below is then enqueued behind a running kernel, and anything that
+    # waited for the device would make the host loop at least that long
+    clock_khz = torch.cuda.get_device_properties(0).clock_rate if hasattr(torch.cuda.get_device_properties(0), "clock_rate") else 1_900_000
+    t0 = time.perf_counter()
+    torch.cuda._sleep(int(0.06 * clock_khz * 1e3))
+    for _ in range(n_batches):
+        zb.decode_and_score(text, tokens, gt, (H, W), meter)
+        meter.get_scores_async()
+        seen.append(meter.poll_scores())
+    host_s = time.perf_counter() - t0
+    still_busy = not torch.cuda.current_stream().query()
+    torch.cuda.synchronize()
+    gpu_s = time.perf_counter() - t0
+    assert still_busy and host_s < 0.05, f"the host loop waited for the device (host {host_s * 1e3:.1f} ms, device done at {gpu_s * 1e3:.1f} ms)"
+    assert all(x is None for x in seen)                              # nothing can land while the device is still asleep
+    meter.get_scores_async(); torch.cuda.synchronize()
+    polled = meter.poll_scores()
+    blocking = meter.get_scores()
+    assert polled is not None and polled[0] == blocking[0] and polled[1] == blocking[1]
+    assert int(meter.counts().sum()) == n_batches * B * H * W
+
+
+@pytest.mark.parametrize("shape", [(2, 100, 15, 20, 512), (3, 37, 9, 7, 96), (1, 100, 60, 80, 512)])
+def test_masked_average_on_tensor_cores_matches_simt_and_reference(zb, shape):
+    """zutis_instance_lowres_stats_ws computes the masked average (zutis.py:404-406) as a mask x tokens contraction on the
+    tcgen05 kernel; sizes and probability sums are the SIMT kernel's, the averages agree with it and with the torch-CPU
+    restatement of the reference's 5-D broadcast to fp32 summation-order accuracy (incl. h*w not a multiple of 32)."""
+    from zutis_b200 import _ffi
+    B, Q, h, w, D = shape
+    gen = torch.Generator().manual_seed(B * 100 + Q)
+    probs = torch.sigmoid(2.0 * torch.randn(B, Q, h, w, generator=gen))
+    probs[0, 0] = 0.1                                                  # an empty mask: 0 / 1e-7 = 0
+    tokens = torch.nn.functional.normalize(torch.randn(B, h, w, D, generator=gen), dim=-1)
+    pc, tc = probs.cuda(), tokens.cuda()
+    sizes, psum, mean = zb.ops.instance_lowres_stats(pc, tc, 0.5)                     # workspace path
+    s2 = torch.empty_like(sizes); p2 = torch.empty_like(psum); m2 = torch.empty_like(mean)
+    _ffi.call("zutis_instance_lowres_stats", pc.data_ptr(), *pc.stride(), tc.data_ptr(), B, Q, h, w, D, 0.5,
+              s2.data_ptr(), p2.data_ptr(), m2.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert torch.equal(sizes, s2) and torch.equal(psum, p2)
+    mask = (probs > 0.5)
+    want = (tokens[:, None] * mask[..., None]).sum(dim=(2, 3)) / (mask.sum(dim=(2, 3)).float()[..., None] + 1e-7)   # the reference's expression
+    scale = float(want.abs().max())
+    assert float((mean.cpu() - want).abs().max()) <= 2e-6 * max(scale, 1.0)
+    assert float((m2.cpu() - want).abs().max()) <= 2e-6 * max(scale, 1.0)
+    assert float(mean[0, 0].abs().max()) == 0.0

@@ -60,6 +60,8 @@ SIGNATURES = {
     "zutis_mask_rle": (_i, [_vp, _l, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "zutis_rle_to_string": (_i, [_vp, _vp, _vp, _i, _vp, _l, _vp, _vp, _vp, _vp]),
     "zutis_instance_lowres_stats": (_i, [_vp, _l, _l, _l, _l, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
+    "zutis_instance_stats_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "zutis_instance_lowres_stats_ws": (_i, [_vp, _l, _l, _l, _l, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "zutis_instance_categories": (_i, [_vp, _l, _vp, _i, _i, _f, _vp, _vp, _vp]),
     "zutis_image_norm_workspace_bytes": (_sz, [_i, _l, _i]),
     "zutis_image_layernorm_l2norm": (_i, [_vp, _i, _l, _i, _i, _f, _f, _vp, _sz, _vp]),

@@ -9,6 +9,7 @@
 //   categories_kernel       sigmoid(T * cos(text, mean token)) -> argmax / max        networks/zutis.py:409-420
 // Compiled with -fmad=false; interpolation uses the same explicit fma pattern as decode_score.cu.
 #include "common.cuh"
+#include "gemm.cuh"
 
 #include <limits.h>
 
@@ -406,6 +407,44 @@ __global__ void __launch_bounds__(256) lowres_stats_kernel(const float* probs, l
     }
 }
 
+
+// ------------------------------------------------------------------ masked average on the tensor cores
+// sum_hw tokens[b,hw,:] * mask[b,q,hw] (zutis.py:404-406, a [B,100,h,w,512] broadcast in the reference) is a
+// [Q, hw] x [hw, D] contraction per image.  The 0/1 mask is exact in any number format and the tokens go through the
+// contraction kernel's hi/lo split, so the sums are fp32-grade.  Both operands must be K-contiguous (K = pixels):
+// the mask is written that way, the channel-last tokens are transposed once.
+__global__ void __launch_bounds__(256) mask_matrix_kernel(const float* probs, long sb, long sq, long sy, long sx, int Q, int h, int w,
+                                                          int hwp, float threshold, float* mask) {
+    const int b = blockIdx.z, q = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hwp) return;
+    float m = 0.0f;
+    if (i < h * w) m = probs[(long)b * sb + (long)q * sq + (long)(i / w) * sy + (long)(i % w) * sx] > threshold ? 1.0f : 0.0f;
+    mask[((long)b * Q + q) * hwp + i] = m;
+}
+
+// tokens [B, hw, D] -> [B, D, hwp] (zero-padded pixels), 32x32 tiles through shared memory
+__global__ void __launch_bounds__(256) transpose_tokens_kernel(const float* tokens, int hw, int D, int hwp, float* out) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int pp = p0 + r, d = d0 + tx;
+        tile[r][tx] = (pp < hw && d < D) ? tokens[((long)b * hw + pp) * D + d] : 0.0f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int d = d0 + r, pp = p0 + tx;
+        if (d < D && pp < hwp) out[((long)b * D + d) * hwp + pp] = tile[tx][r];
+    }
+}
+
+__global__ void __launch_bounds__(256) divide_rows_kernel(float* sums, const int* sizes, long n_rows, int D) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_rows * D) sums[i] = sums[i] / __fadd_rn((float)sizes[i / D], 1e-7f);       // (mask_sizes + 1e-7), zutis.py:406
+}
+
 // block per (b,q): cosine of the mean token with every text row, sigmoid(T*cos), first-max category
 // (networks/zutis.py:409-420).  A warp takes one category at a time: lanes stride the channel dimension (coalesced
 // reads of the text row), partial sums are combined by a shuffle tree.
@@ -568,6 +607,52 @@ extern "C" int zutis_instance_lowres_stats(const float* probs, long sb, long sq,
     lowres_stats_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(probs, sb, sq, sy, sx, tokens, Q, h, w, D, threshold,
                                                                        sizes, psum, mean_tokens);
     return check_launch("lowres_stats_kernel");
+}
+
+
+extern "C" size_t zutis_instance_stats_workspace_bytes(int B, int Q, int h, int w, int D) {
+    if (B <= 0 || Q <= 0 || h <= 0 || w <= 0 || D <= 0) return 0;
+    const long hwp = ((long)h * w + 31) & ~31L;
+    const size_t mask = (size_t)B * Q * hwp * 4, tok = (size_t)B * D * hwp * 4;
+    const size_t gemm = gemm_tcgen05_workspace_bytes(Q, D, (int)hwp, B, ZUTIS_GEMM_TF32X3);
+    return ((mask + 255) & ~(size_t)255) + ((tok + 255) & ~(size_t)255) + gemm;
+}
+
+extern "C" int zutis_instance_lowres_stats_ws(const float* probs, long sb, long sq, long sy, long sx,
+                                              const float* tokens, int B, int Q, int h, int w, int D,
+                                              float threshold, int32_t* sizes, float* psum, float* mean_tokens,
+                                              void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    // sizes and in-mask probability sums: the statistics kernel without its token phase
+    int st = zutis_instance_lowres_stats(probs, sb, sq, sy, sx, nullptr, B, Q, h, w, 0, threshold, sizes, psum, nullptr, stream_);
+    if (st != ZUTIS_OK || !mean_tokens) return st;
+    ZUTIS_REQUIRE(tokens && D > 0, "zutis_instance_lowres_stats_ws: mean_tokens needs tokens and D");
+    const long hw = (long)h * w, hwp = (hw + 31) & ~31L;
+    GemmParams g;
+    const size_t mask_bytes = ((size_t)B * Q * hwp * 4 + 255) & ~(size_t)255, tok_bytes = ((size_t)B * D * hwp * 4 + 255) & ~(size_t)255;
+    const size_t need = zutis_instance_stats_workspace_bytes(B, Q, h, w, D);
+    float* mask = reinterpret_cast<float*>(workspace);
+    float* tokT = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + mask_bytes);
+    g.A = mask; g.lda = hwp; g.strideA = (long)Q * hwp;
+    g.Bm = tokT; g.ldb = hwp; g.strideB = (long)D * hwp;
+    g.C = mean_tokens; g.stride_cn = D; g.stride_cp = 1; g.strideC = (long)Q * D;
+    g.M = Q; g.N = D; g.K = (int)hwp; g.sigmoid = 0;
+    const bool tensor_path = workspace && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
+                             hwp < 2147483647L && B <= 65535 && Q <= 65535 && gemm_tcgen05_supports(g, B, ZUTIS_GEMM_TF32X3);
+    if (!tensor_path)      // no (or too small a) workspace, or a shape the contraction kernel does not take: the SIMT kernel
+        return zutis_instance_lowres_stats(probs, sb, sq, sy, sx, tokens, B, Q, h, w, D, threshold, sizes, psum, mean_tokens, stream_);
+    mask_matrix_kernel<<<dim3((unsigned)((hwp + 255) / 256), (unsigned)Q, (unsigned)B), 256, 0, stream>>>(probs, sb, sq, sy, sx, Q, h, w, (int)hwp, threshold, mask);
+    st = check_launch("mask_matrix_kernel");
+    if (st != ZUTIS_OK) return st;
+    transpose_tokens_kernel<<<dim3((unsigned)(hwp / 32), (unsigned)((D + 31) / 32), (unsigned)B), 256, 0, stream>>>(tokens, (int)hw, D, (int)hwp, tokT);
+    st = check_launch("transpose_tokens_kernel");
+    if (st != ZUTIS_OK) return st;
+    st = launch_gemm_tcgen05(g, B, ZUTIS_GEMM_TF32X3, reinterpret_cast<char*>(workspace) + mask_bytes + tok_bytes,
+                             workspace_bytes - mask_bytes - tok_bytes, stream);
+    if (st != ZUTIS_OK) return st;
+    const long n = (long)B * Q * D;
+    divide_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(mean_tokens, sizes, (long)B * Q, D);
+    return check_launch("divide_rows_kernel");
 }
 
 extern "C" int zutis_instance_categories(const float* mean_tokens, long n_rows, const float* text, int n_categories, int D,

@@ -364,9 +364,13 @@ def instance_lowres_stats(probs: torch.Tensor, tokens: Optional[torch.Tensor], t
         D = tokens.shape[-1]
         mean = torch.empty((B, Q, D), device=probs.device, dtype=torch.float32)
     with torch.cuda.device(probs.device):
-        F.call("zutis_instance_lowres_stats", probs.data_ptr(), probs.stride(0), probs.stride(1), probs.stride(2), probs.stride(3),
+        # the masked average runs on the tensor cores (mask x tokens contraction); scratch: mask matrix, transposed tokens, operand split
+        ws_bytes = F.lib().zutis_instance_stats_workspace_bytes(B, Q, h, w, D) if tokens is not None else 0
+        ws = torch.empty(ws_bytes, device=probs.device, dtype=torch.uint8) if ws_bytes else None
+        F.call("zutis_instance_lowres_stats_ws", probs.data_ptr(), probs.stride(0), probs.stride(1), probs.stride(2), probs.stride(3),
                tokens.data_ptr() if tokens is not None else None, B, Q, h, w, D, float(threshold),
-               sizes.data_ptr(), psum.data_ptr(), mean.data_ptr() if mean is not None else None, _stream())
+               sizes.data_ptr(), psum.data_ptr(), mean.data_ptr() if mean is not None else None,
+               ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
     return sizes, psum, mean
 
 

@@ -35,6 +35,10 @@ class RunningScore(object):
         self._partial = torch.zeros(n2, dtype=torch.int32, device=self.device)     # per-launch partial
         self._pending = 0          # pixels counted into the partial since the last merge
         self._host_extra = None    # float64 matrix assigned by a caller through the attribute, if any
+        # non-blocking read-out (get_scores_async / poll_scores): pinned host mirror of the matrix + completion event
+        self._pinned = None
+        self._copy_event = None
+        self._last_scores = None
 
     # ------------------------------------------------------------------ device-side plumbing
     def _as_device_labels(self, x) -> torch.Tensor:
@@ -132,13 +136,48 @@ class RunningScore(object):
         self._hist.zero_(); self._partial.zero_(); self._pending = 0
         self._host_extra = value.copy()
 
+    # ------------------------------------------------------------------ non-blocking read-out (additive)
+    def get_scores_async(self) -> None:
+        """Enqueue merge + device-to-host copy of the matrix into pinned memory and return at once.
+
+        For callers that refresh a progress bar every batch (trainer.py:178, :348): the copy rides the stream behind
+        the batch's kernels, nothing waits for it, and ``poll_scores()`` hands out the scores of the most recent copy
+        that has completed.  A copy still in flight is not overtaken: a second request before it lands is dropped."""
+        if self._copy_event is not None and not self._copy_event.query():
+            return
+        self._harvest()
+        self._merge()
+        if self._pinned is None:
+            self._pinned = torch.empty(self._hist.shape, dtype=torch.int64, pin_memory=True)
+        self._pinned.copy_(self._hist, non_blocking=True)
+        self._copy_event = torch.cuda.Event()
+        self._copy_event.record(torch.cuda.current_stream(self.device))
+
+    def _harvest(self) -> None:
+        if self._copy_event is not None and self._copy_event.query():
+            m = self._pinned.numpy().astype(np.float64).reshape(self.n_classes, self.n_classes)
+            if self._host_extra is not None:
+                m = m + self._host_extra
+            self._last_scores = self._scores_of(m)
+            self._copy_event = None
+
+    def poll_scores(self) -> Optional[Tuple[Dict[str, float], Dict[int, float]]]:
+        """Scores of the latest completed ``get_scores_async`` copy (None until one has landed).  Never blocks."""
+        self._harvest()
+        return self._last_scores
+
     def get_scores(self) -> Tuple[Dict[str, float], Dict[int, float]]:
         """Pixel / mean / frequency-weighted accuracy and mean IoU (running_score.py:22-47).
 
         float64 numpy on the n x n matrix, same operations in the same order as the reference, so
         equal counts give bit-identical scores (NaN for absent classes, skipped by nanmean).
+        Synchronises (it returns numbers); see ``get_scores_async`` / ``poll_scores`` for per-batch polling.
         """
-        m = self.confusion_matrix
+        return self._scores_of(self.confusion_matrix)
+
+    @staticmethod
+    def _scores_of(m: np.ndarray) -> Tuple[Dict[str, float], Dict[int, float]]:
+        n_classes = m.shape[0]
         diag = np.diag(m)
         rows = m.sum(axis=1)
         cols = m.sum(axis=0)
@@ -155,7 +194,7 @@ class RunningScore(object):
         fwavacc = (freq[freq > 0] * iu[freq > 0]).sum()
         return (
             {"Pixel Acc": acc, "Mean Acc": acc_cls, "FreqW Acc": fwavacc, "Mean IoU": mean_iu},
-            dict(zip(range(self.n_classes), iu)),
+            dict(zip(range(n_classes), iu)),
         )
 
     def reset(self) -> None:
@@ -163,3 +202,5 @@ class RunningScore(object):
         self._partial.zero_()
         self._pending = 0
         self._host_extra = None
+        self._copy_event = None
+        self._last_scores = None

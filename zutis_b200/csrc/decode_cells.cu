@@ -33,8 +33,7 @@
 // its survivors, and SMs differ); each warp requests its run two iterations ahead, and the last CTA re-arms the counter.
 // Without a workspace, cell rows go round-robin to CTAs and a shared-memory counter hands a CTA's runs to its warps.
 // More than 128 categories (NI = 0): the taps are read from global memory instead (a run's taps would not fit).
-#include "decode.cuh"
-#include "tma.cuh"
+#include "cells.cuh"
 
 namespace zutis {
 
@@ -43,108 +42,14 @@ namespace {
 constexpr int kRunCells = 4;       // cells per run = 32 lanes / 8 slices
 constexpr int kSlices = 8;
 constexpr int kBoxPixels = kRunCells + 1;
-constexpr unsigned kFull = 0xffffffffu;
 constexpr int kCellWarpsMax = 20;   // 640 threads: 96 registers per thread, no spills (80 registers spill; the spills go to L2 because shared memory leaves no L1)
 
-// Make a value opaque to the optimiser: it stays in its register instead of being re-derived from kernel parameters
-// and special registers at every use (the compiler otherwise rematerialises shared-memory base addresses all over).
-#define ZUTIS_KEEP(x) asm volatile("" : "+r"(x))
-
-__device__ __forceinline__ bool elect_one_lane() {
-    uint32_t pred;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "elect.sync _|p, 0xffffffff;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(pred));
-    return pred != 0;
-}
-
-// 0 <= g < n as one unsigned compare (running_score.py:12)
-template <typename GT>
-__device__ __forceinline__ bool label_in_range(GT g, int n) { return (unsigned long long)(long long)g < (unsigned long long)n; }
-
-__device__ __forceinline__ float min3(float a, float b, float c) {
-    float r;
-    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-    return r;
-}
-__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long f4_lo(const float4& v) { return pack2(v.x, v.y); }
-__device__ __forceinline__ unsigned long long f4_hi(const float4& v) { return pack2(v.z, v.w); }
-__device__ __forceinline__ float4 lds128(uint32_t a) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ float lds32(uint32_t a) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ unsigned lds_u32(uint32_t a) {
-    unsigned v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ float2 lds_f2(uint32_t a) {
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ unsigned lds_u16(uint32_t a) {
-    unsigned v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
-}
-// predicated store: no branch, whatever the compiler thinks of the condition
-__device__ __forceinline__ void sts_u16_if(bool cond, uint32_t a, unsigned v) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.u32 p, %2, 0;\n"
-        "@p st.shared.u16 [%0], %1;\n"
-        "}\n"
-        ::"r"(a), "h"((unsigned short)v), "r"((unsigned)cond) : "memory");
-}
-
-__device__ __forceinline__ void red_shared_add(uint32_t a, int v) {
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-template <typename GT> struct Pair;
-template <> struct Pair<uint8_t> { typedef uchar2 type; };
-template <> struct Pair<int16_t> { typedef short2 type; };
-template <> struct Pair<int32_t> { typedef int2 type; };
-template <> struct Pair<long long> { typedef longlong2 type; };
-
-// n / d for n < 2^31 with a divisor fixed per launch: q = umulhi(n, mul) >> shr (mul == 0: d == 1)
-struct FastDiv {
-    unsigned mul, shr;
-};
-__device__ __forceinline__ unsigned fast_div(unsigned n, FastDiv f) { return f.mul ? (__umulhi(n, f.mul) >> f.shr) : n; }
-FastDiv make_fast_div(unsigned d) {
-    FastDiv f;
-    if (d <= 1) { f.mul = 0; f.shr = 0; return f; }
-    unsigned l = 0;
-    while ((1u << l) < d) ++l;
-    const unsigned p = 31 + l;
-    f.mul = (unsigned)((((unsigned long long)1 << p) + d - 1) / d);
-    f.shr = p - 32;
-    return f;
-}
-
 }  // namespace
+
+// Cell rows of an image are visited from the borders inwards (0, h-1, 1, h-2, ...): the clamped border rows are taller than
+// 8 pixels and take the slower general path, and work handed out last should be short (the kernel ends when the last
+// run ends).
+__device__ __forceinline__ int border_first(int k, int h) { return (k & 1) ? h - 1 - (k >> 1) : (k >> 1); }
 
 struct CellParams {
     const float* logits;
@@ -256,7 +161,7 @@ __global__ void __launch_bounds__(kCellWarpsMax * 32, 1) decode_cells_kernel(con
     auto issue_taps = [&](unsigned row, int cxb) {
         if (STAGED) {
             const unsigned b = fast_div(row, p.div_h);
-            const int cy = (int)(row - b * (unsigned)p.h);
+            const int cy = border_first((int)(row - b * (unsigned)p.h), p.h);
             if (elect_one_lane()) {
                 mbarrier_arrive_expect_tx(bar, (uint32_t)(2 * kBoxPixels) * (uint32_t)p.tap_pitch_bytes);
                 tma_load_4d(tap_base, &tap_map, bar, 0, cxb, cy, (int)b);
@@ -273,7 +178,7 @@ __global__ void __launch_bounds__(kCellWarpsMax * 32, 1) decode_cells_kernel(con
 
     while (cur_row != 0xffffffffu) {
         const int b = (int)fast_div(cur_row, p.div_h);
-        const int cy = (int)(cur_row - (unsigned)b * (unsigned)p.h), cx_begin = cur_cxb;
+        const int cy = border_first((int)(cur_row - (unsigned)b * (unsigned)p.h), p.h), cx_begin = cur_cxb;
         const int cy1 = min(cy + 1, p.h - 1);
         const int maxslot = min(kRunCells, p.w - 1 - cx_begin);                // last pixel of the box that exists
         const uint32_t lower = (STAGED && cy1 != cy) ? (uint32_t)(kBoxPixels * p.tap_pitch_bytes) : 0u;
@@ -453,7 +358,7 @@ __global__ void __launch_bounds__(kCellWarpsMax * 32, 1) decode_cells_kernel(con
             if (p.hist) {
                 // pull the next run's ground truth towards L2: lane = (row of 8, 128-byte segment of 4)
                 const unsigned nb = fast_div(nxt_row, p.div_h);
-                const int ncy = (int)(nxt_row - nb * (unsigned)p.h);
+                const int ncy = border_first((int)(nxt_row - nb * (unsigned)p.h), p.h);
                 const int nys = (int)lds_u32(a_ystart + (uint32_t)ncy * 4u);
                 const int nxs = (int)lds_u32(a_xstart + (uint32_t)nxt_cxb * 4u);
                 const int nxe = (int)lds_u32(a_xstart + (uint32_t)min(nxt_cxb + kRunCells, p.w) * 4u);

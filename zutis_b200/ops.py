@@ -73,7 +73,8 @@ class DecodeWorkspace:
         key = (str(device), _stream())
         buf = self.bufs.get(key)
         if buf is None or buf.numel() < nbytes:
-            buf = self.bufs[key] = torch.zeros(max(nbytes, 16), device=device, dtype=torch.uint8)
+            buf = self.bufs[key] = torch.empty(max(nbytes, 256), device=device, dtype=torch.uint8)
+            buf[:256].zero_()
         return buf
 
 

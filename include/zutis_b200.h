@@ -167,6 +167,16 @@ ZUTIS_API int zutis_unpack_mask_bits(const uint32_t* mask_bits, long n_masks, in
 ZUTIS_API int zutis_pairwise_mask_intersections(const uint32_t* mask_bits, int M, long words_per_mask,
                                                 int32_t* inter, void* stream);
 
+/* Greedy per-category hard NMS on the device (networks/zutis.py:245-278, nms_type="hard"), driven by the intersection
+ * counts of zutis_pairwise_mask_intersections for B images ([B,M,M], diagonal = areas).
+ * categories [B,M] int32 (0 = background, skipped), scores [B,M] fp32 (hard NMS leaves them unchanged).
+ * pick_rank[b,i] = round in which mask i was chosen for its category (emission order inside the category), -1 when it
+ * was suppressed (IoU with a chosen mask > iou_threshold, float64 like utils/iou.py) or dropped (score <= score_floor
+ * after the first pick).  tie[b] != 0: two candidates of a category had equal scores at a pick -- the reference's choice
+ * then follows numpy's unstable argsort and the caller should replay that image with the reference loop. */
+ZUTIS_API int zutis_instance_nms_hard(const int32_t* inter, const int32_t* categories, const float* scores, int B, int M,
+                                      double iou_threshold, float score_floor, int32_t* pick_rank, int32_t* tie, void* stream);
+
 /* COCO run-length encoding + bounding boxes of bit-packed masks, on the device.
  * Replaces pycocotools.mask.encode(np.asfortranarray(m)) (networks/zutis.py:290; cocoapi rleEncode: the mask flattened
  * column by column, alternating run lengths starting with a possibly empty run of zeros) and

@@ -528,6 +528,40 @@ def _pack_rows(masks: np.ndarray) -> np.ndarray:
     padded[:, :, :W] = masks
     return np.packbits(padded.reshape(n, H, words, 32), axis=-1, bitorder="little").view(np.uint32).reshape(n, H, words).view(np.int32)
 
+def test_device_hard_nms_matches_reference_loop(zb):
+    """The device suppression (ops.instance_nms_hard) against the host replay of zutis.py:232-282 on random overlapping
+    masks: few categories so that chains of suppression are long, low scores around the 0.001 floor, empty masks, a
+    background category, and -- flagged, not resolved -- duplicated scores."""
+    from zutis_b200.decode import _nms_keep, _ordered_picks
+    rng = np.random.default_rng(21)
+    for trial, (B, M, n_cat) in enumerate([(3, 40, 3), (2, 100, 5), (1, 7, 2), (2, 64, 1), (1, 1, 2)]):
+        H, W = 24, 40
+        masks = np.zeros((B, M, H, W), bool)
+        for b in range(B):
+            for i in range(M):
+                if rng.random() < 0.1:
+                    continue                                   # empty mask
+                y0, x0 = rng.integers(0, H - 4), rng.integers(0, W - 4)
+                masks[b, i, y0:y0 + rng.integers(2, 12), x0:x0 + rng.integers(2, 16)] = True
+        cats = rng.integers(0, n_cat + 1, (B, M)).astype(np.int64)
+        scores = rng.random((B, M)).astype(np.float32)
+        scores[rng.random((B, M)) < 0.2] *= np.float32(0.002)       # around the floor
+        if trial == 3:
+            scores[1, 5] = scores[1, 9]; cats[1, 5] = cats[1, 9] = 1   # a tie inside one category
+        bits = torch.from_numpy(np.stack([_pack_rows(m) for m in masks])).cuda()
+        inter = torch.stack([zb.ops.pairwise_mask_intersections(bits[b]) for b in range(B)])
+        pick, tie = zb.ops.instance_nms_hard(inter, torch.from_numpy(cats).to(torch.int32).cuda(), torch.from_numpy(scores).cuda())
+        pick, tie, inter_h = pick.cpu().numpy(), tie.cpu().numpy(), inter.cpu().numpy()
+        for b in range(B):
+            if trial == 3 and b == 1:
+                assert tie[b] != 0
+                continue
+            assert tie[b] == 0
+            want = _nms_keep(cats[b], scores[b], inter_h[b], "hard")
+            got = _ordered_picks(cats[b], scores[b], pick[b], inter_h[b].diagonal())
+            assert [(int(c), q, float(s)) for c, q, s in got] == [(int(c), q, float(s)) for c, q, s in want]
+
+
 
 @pytest.mark.parametrize("H,W", [(1, 1), (1, 70), (33, 1), (5, 32), (31, 33), (64, 64), (50, 70), (480, 640), (97, 1000)])
 def test_mask_rle_and_boxes_match_oracle(zb, H, W):

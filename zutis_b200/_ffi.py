@@ -57,6 +57,7 @@ SIGNATURES = {
     "zutis_decode_threshold": (_i, [_vp, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "zutis_unpack_mask_bits": (_i, [_vp, _l, _i, _i, _vp, _vp]),
     "zutis_pairwise_mask_intersections": (_i, [_vp, _i, _l, _vp, _vp]),
+    "zutis_instance_nms_hard": (_i, [_vp, _vp, _vp, _i, _i, C.c_double, _f, _vp, _vp, _vp]),
     "zutis_mask_rle": (_i, [_vp, _l, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "zutis_rle_to_string": (_i, [_vp, _vp, _vp, _i, _vp, _l, _vp, _vp, _vp, _vp]),
     "zutis_instance_lowres_stats": (_i, [_vp, _l, _l, _l, _l, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),

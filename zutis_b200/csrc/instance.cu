@@ -100,6 +100,75 @@ __global__ void __launch_bounds__(256) pair_inter_kernel(const uint32_t* bits, i
     }
 }
 
+
+// Greedy hard NMS per category (networks/zutis.py:245-278), one block per image, driven by the intersection counts.
+// Every category advances at once: in a round, thread i is picked when it is the highest-scoring live candidate of its
+// category; the picked mask then suppresses the live masks of its category whose IoU with it exceeds the threshold
+// (IoU = both / ((area_i + area_top - both) + 1e-7) in float64, as utils/iou.py:31-33 computes it), and whatever is
+// left with a score <= floor is dropped, exactly like the reference's `if s > 0.001` after the first pick.
+// pick_rank[i] = the round in which i was picked (-1: suppressed or dropped); scores are unchanged by hard NMS.
+// tie[b] is set when two live candidates of a category carry the same score at a pick: the reference's order then
+// depends on numpy's unstable argsort, and the caller replays that image on the host.
+__global__ void __launch_bounds__(128) nms_hard_kernel(const int* __restrict__ inter, const int* __restrict__ cats, const float* __restrict__ scores,
+                                                       int M, double iou_threshold, float floor, int* __restrict__ pick_rank, int* __restrict__ tie) {
+    extern __shared__ int s_mem[];
+    int* s_cat = s_mem;                       // [M]
+    float* s_score = reinterpret_cast<float*>(s_mem + M);
+    int* s_live = s_mem + 2 * M;              // [M] 1 = candidate still in play
+    int* s_top = s_mem + 3 * M;               // [M] the query picked for this thread's category in the current round (-1: none)
+    __shared__ int s_any, s_tie;
+    const int b = blockIdx.x;
+    const int* in = inter + (long)b * M * M;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        s_cat[i] = cats[(long)b * M + i];
+        s_score[i] = scores[(long)b * M + i];
+        s_live[i] = s_cat[i] != 0;            // the background category is skipped (zutis.py:246)
+        pick_rank[(long)b * M + i] = -1;
+    }
+    if (threadIdx.x == 0) s_tie = 0;
+    __syncthreads();
+    for (int round = 0; round < M; ++round) {
+        if (threadIdx.x == 0) s_any = 0;
+        __syncthreads();
+        // who is the top of its category?
+        for (int i = threadIdx.x; i < M; i += blockDim.x) {
+            bool top = s_live[i] != 0;
+            if (top) {
+                const float si = s_score[i];
+                if (si != si) s_tie = 1;      // NaN scores have no order: host replay
+                for (int j = 0; j < M; ++j) {
+                    if (j == i || !s_live[j] || s_cat[j] != s_cat[i]) continue;
+                    const float sj = s_score[j];
+                    if (sj > si) { top = false; break; }
+                    if (sj == si) { s_tie = 1; if (j < i) { top = false; break; } }      // flagged; any deterministic choice
+                }
+            }
+            s_top[i] = top ? 1 : 0;
+            if (top) s_any = 1;
+        }
+        __syncthreads();
+        if (!s_any) break;
+        // the picks leave the game; everything else in their category is tested against them
+        for (int i = threadIdx.x; i < M; i += blockDim.x) {
+            if (s_top[i]) { pick_rank[(long)b * M + i] = round; continue; }
+            if (!s_live[i]) continue;
+            int t = -1;
+            for (int j = 0; j < M; ++j)
+                if (s_top[j] && s_cat[j] == s_cat[i]) { t = j; break; }
+            if (t < 0) continue;
+            const int both = in[(long)i * M + t];
+            const double iou = (double)both / ((double)(in[(long)i * M + i] + in[(long)t * M + t] - both) + 1e-7);
+            const float s_new = iou > iou_threshold ? 0.0f : s_score[i];                  // s * weight, weight in {0, 1}
+            if (!(s_new > floor)) s_live[i] = 0;                                           // `if s > 0.001` (zutis.py:274)
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < M; i += blockDim.x)
+            if (s_top[i]) s_live[i] = 0;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tie[b] = s_tie;
+}
+
 // COCO run-length encoding and bounding box of bit-packed masks, on the device.
 // Replaces, per kept mask, pycocotools.mask.encode(np.asfortranarray(m)) (networks/zutis.py:290; the run lengths that
 // cocoapi's rleEncode produces: the mask flattened COLUMN by column, alternating runs starting with a zero run that
@@ -552,6 +621,18 @@ extern "C" int zutis_pairwise_mask_intersections(const uint32_t* mask_bits, int 
     if (st != ZUTIS_OK) return st;
     pair_inter_kernel<<<dim3(M, M), 256, 0, (cudaStream_t)stream>>>(mask_bits, M, words_per_mask, inter);
     return check_launch("pair_inter_kernel");
+}
+
+
+extern "C" int zutis_instance_nms_hard(const int32_t* inter, const int32_t* categories, const float* scores, int B, int M,
+                                       double iou_threshold, float score_floor, int32_t* pick_rank, int32_t* tie, void* stream) {
+    ZUTIS_REQUIRE(inter && categories && scores && pick_rank && tie, "zutis_instance_nms_hard: NULL pointer");
+    ZUTIS_REQUIRE(B > 0 && M > 0 && M <= 8192, "zutis_instance_nms_hard: bad shape B=%d M=%d", B, M);
+    int st = current_device_ok();
+    if (st != ZUTIS_OK) return st;
+    // the reference compares `iou > 0.3` with both sides in float64, and `s > 0.001` in float32
+    nms_hard_kernel<<<(unsigned)B, 128, (size_t)M * 16, (cudaStream_t)stream>>>(inter, categories, scores, M, iou_threshold, score_floor, pick_rank, tie);
+    return check_launch("nms_hard_kernel");
 }
 
 extern "C" int zutis_mask_rle(const uint32_t* mask_bits, long mask_stride_words, const int32_t* mask_ids, int n_masks,

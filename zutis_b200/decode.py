@@ -128,6 +128,22 @@ def _nms_keep(cats: np.ndarray, scores: np.ndarray, inter: np.ndarray, nms_type:
     return kept
 
 
+def _ordered_picks(cats: np.ndarray, scores: np.ndarray, pick_rank: np.ndarray, areas: np.ndarray):
+    """Device NMS result (ops.instance_nms_hard) in the reference's emission order: categories as ``set(cats)`` iterates
+    them (zutis.py:232), and inside a category the masks in the order they were picked; empty masks are skipped (:280)."""
+    kept = []
+    chosen = np.nonzero(pick_rank >= 0)[0]
+    for cat in set(cats):
+        if cat == 0:
+            continue
+        mine = chosen[cats[chosen] == cat]
+        for i in mine[np.argsort(pick_rank[mine], kind="stable")]:
+            if areas[i] == 0:
+                continue
+            kept.append((cat, int(i), scores[i]))
+    return kept
+
+
 @torch.no_grad()
 def predict(
         self,
@@ -178,18 +194,33 @@ def predict(
 
     if image_ids is None:
         image_ids = [0 for _ in range(B)]
-    # pairwise intersection counts of every image are enqueued first and fetched with one copy
+    # pairwise intersection counts of every image, enqueued back to back; they stay on the device unless a host replay needs them
     inter_dev = torch.stack([ops.pairwise_mask_intersections(bits[b]) for b in range(B)])
-    inter_all = inter_dev.cpu().numpy()
+    n_images = min(B, len(image_ids))                               # the reference zips range(B) with image_ids
     kept: List[Tuple[int, int, int, float]] = []                   # (image, query, category, score), reference order
-    for b in range(min(B, len(image_ids))):                         # the reference zips range(B) with image_ids
-        cats_b, conf_b = category_ids[b], confidence[b]
-        if nms_type is None:
-            areas = inter_all[b].diagonal()
-            keep = [(c, q, s) for q, (s, c) in enumerate(zip(conf_b, cats_b)) if areas[q] != 0 and c != 0]
-        else:
-            keep = _nms_keep(cats_b, conf_b, inter_all[b], nms_type)
-        kept.extend((b, q, c, s) for c, q, s in keep)
+    if nms_type == "hard":
+        # greedy per-category suppression on the device; only areas, pick order and the tie flags come back
+        pick_dev, tie_dev = ops.instance_nms_hard(inter_dev, cat_dev.to(torch.int32), torch.from_numpy(confidence).to(inter_dev.device))
+        areas_all = torch.diagonal(inter_dev, dim1=1, dim2=2).cpu().numpy()
+        pick_all, tie_all = pick_dev.cpu().numpy(), tie_dev.cpu().numpy()
+        for b in range(n_images):
+            cats_b, conf_b = category_ids[b], confidence[b]
+            if tie_all[b]:
+                # equal scores inside a category: the reference's pick follows numpy's argsort, replay its loop
+                keep = _nms_keep(cats_b, conf_b, inter_dev[b].cpu().numpy(), nms_type)
+            else:
+                keep = _ordered_picks(cats_b, conf_b, pick_all[b], areas_all[b])
+            kept.extend((b, q, c, s) for c, q, s in keep)
+    else:
+        inter_all = inter_dev.cpu().numpy()
+        for b in range(n_images):
+            cats_b, conf_b = category_ids[b], confidence[b]
+            if nms_type is None:
+                areas = inter_all[b].diagonal()
+                keep = [(c, q, s) for q, (s, c) in enumerate(zip(conf_b, cats_b)) if areas[q] != 0 and c != 0]
+            else:
+                keep = _nms_keep(cats_b, conf_b, inter_all[b], nms_type)
+            kept.extend((b, q, c, s) for c, q, s in keep)
     predictions: List[dict] = list()
     if not kept:
         return predictions

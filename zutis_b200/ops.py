@@ -276,6 +276,20 @@ def pairwise_mask_intersections(bits: torch.Tensor) -> torch.Tensor:
     return inter
 
 
+def instance_nms_hard(inter: torch.Tensor, categories: torch.Tensor, scores: torch.Tensor, iou_threshold: float = 0.3,
+                      score_floor: float = 0.001):
+    """Greedy per-category hard NMS (zutis.py:245-278) for a batch: inter int32 [B,M,M] (diagonal = areas), categories
+    int32 [B,M], scores fp32 [B,M], all on the device.  Returns (pick_rank int32 [B,M], tie int32 [B])."""
+    _need_cuda(inter, "inter")
+    B, M = categories.shape
+    pick = torch.empty((B, M), device=inter.device, dtype=torch.int32)
+    tie = torch.empty((B,), device=inter.device, dtype=torch.int32)
+    with torch.cuda.device(inter.device):
+        F.call("zutis_instance_nms_hard", inter.contiguous().data_ptr(), categories.contiguous().data_ptr(), scores.contiguous().data_ptr(),
+               B, M, float(iou_threshold), float(score_floor), pick.data_ptr(), tie.data_ptr(), _stream())
+    return pick, tie
+
+
 def _mask_rle_device(bits: torch.Tensor, W: int, mask_ids: Optional[torch.Tensor]):
     """Both passes of zutis_mask_rle; everything but the run counts stays on the device."""
     _need_cuda(bits, "bits")

@@ -73,6 +73,7 @@ def parse_args():
                     help="decode kernel: auto = exact per-cell candidate pruning (cells) when the shape allows")
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="one stream: contraction and decode of a step back to back, steps back to back")
     ap.add_argument("--no-extras", action="store_true", help="skip strong scaling, all-reduce timing and the other configs")
     return ap.parse_args()
 
@@ -326,7 +327,7 @@ class SemanticRunner:
     """Device-resident state of the semantic path for one config and one batch size: rotating input sets, the logits /
     labels / workspace buffers and the two C-ABI launches of a step."""
 
-    def __init__(self, cfg, device, seed0, tmode, precision="auto", decode="auto", n_sets=None, image_slice=None):
+    def __init__(self, cfg, device, seed0, tmode, precision="auto", decode="auto", n_sets=None, image_slice=None, pipelined=False):
         import torch
         import zutis_b200
         from zutis_b200 import _ffi, ops
@@ -344,8 +345,17 @@ class SemanticRunner:
         self.text = self.sets[0][0]
         self.meter = zutis_b200.RunningScore(Q, device=device)
         self.Qp = Qp = (Q + 3) & ~3
-        self.logits_buf = torch.zeros(B, h, w, Qp, device=device)
+        # pipelined: the contraction of step i+1 runs on its own stream while step i is decoded (two logits buffers);
+        # both kernels own a whole SM, so what overlaps is one kernel's tail and launch ramp with the other's body
+        self.pipelined = pipelined
+        self.logits_bufs = [torch.zeros(B, h, w, Qp, device=device) for _ in range(2 if pipelined else 1)]
+        self.logits_buf = self.logits_bufs[0]
         self.logits = self.logits_buf[..., :Q].permute(0, 3, 1, 2)
+        self.logits_views = [b[..., :Q].permute(0, 3, 1, 2) for b in self.logits_bufs]
+        if pipelined:
+            self.gemm_stream = torch.cuda.Stream(device=device)
+            self.gemm_done = [torch.cuda.Event() for _ in range(2)]
+            self.decode_done = [None, None]
         self.labels = torch.empty(B, H, W, dtype=torch.int16, device=device)
         self.lib = lib = _ffi.lib()
         flags = ops.gemm_flags(precision)
@@ -364,7 +374,7 @@ class SemanticRunner:
         self.merges = 0
         torch.cuda.synchronize()
 
-    def _gemm(self, flags, tokens, probe=False):
+    def _gemm(self, flags, tokens, probe=False, out=None, stream=None):
         c = self.cfg
         Q, D, h, w = c["Q"], c["D"], c["h"], c["w"]
         torch = self.torch
@@ -373,21 +383,42 @@ class SemanticRunner:
             ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=self.device)
         else:
             wsb, ws = self.ws_bytes, self.ws
-        return self.lib.zutis_gemm_logits(self.text.data_ptr(), D, 0, tokens.data_ptr(), D, h * w * D, self.logits_buf.data_ptr(), 1, self.Qp,
-                                          h * w * self.Qp, Q, h * w, D, self.B, flags, ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream)
+        out = self.logits_buf if out is None else out
+        stream = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        return self.lib.zutis_gemm_logits(self.text.data_ptr(), D, 0, tokens.data_ptr(), D, h * w * D, out.data_ptr(), 1, self.Qp,
+                                          h * w * self.Qp, Q, h * w, D, self.B, flags, ws.data_ptr(), wsb, stream)
 
     def step(self, i, ev=None, merge_now=False):
+        """ev: [contraction start, contraction end, decode start, decode end, merge end], each on the stream its kernel runs on."""
         c, F = self.cfg, self.F
         Q, h, w, H, W = c["Q"], c["h"], c["w"], c["H"], c["W"]
         _, tokens, gt = self.sets[i % self.n_sets]
-        stream = self.torch.cuda.current_stream().cuda_stream
-        if ev: ev[0].record()
-        F.check(self._gemm(self.step_flags, tokens))
-        if ev: ev[1].record()
+        cur = self.torch.cuda.current_stream()
+        stream = cur.cuda_stream
+        if self.pipelined:
+            k = i & 1
+            buf, gs = self.logits_bufs[k], self.gemm_stream
+            if self.decode_done[k] is not None:
+                gs.wait_event(self.decode_done[k])              # logits buffer k was last read by the decode of step i-2
+            if ev: ev[0].record(gs)
+            F.check(self._gemm(self.step_flags, tokens, out=buf, stream=gs.cuda_stream))
+            if ev: ev[1].record(gs)
+            self.gemm_done[k].record(gs)
+            cur.wait_event(self.gemm_done[k])
+            self.logits_buf, self.logits = buf, self.logits_views[k]
+        else:
+            if ev: ev[0].record()
+            F.check(self._gemm(self.step_flags, tokens))
+            if ev: ev[1].record()
+        if ev: ev[2].record()
         F.check(self.lib.zutis_decode_score_ws(self.logits.data_ptr(), h * w * self.Qp, 1, w * self.Qp, self.Qp, self.B, Q, h, w, H, W,
                                                gt.data_ptr(), F.GT_I64, H * W, self.labels.data_ptr(), self.meter._partial.data_ptr(), Q,
                                                self.decode_mode | F.DECODE_WORKSPACE_ZEROED, self.dws.data_ptr(), self.dws_bytes, stream))
-        if ev: ev[2].record()
+        if ev: ev[3].record()
+        if self.pipelined:
+            if self.decode_done[k] is None:
+                self.decode_done[k] = self.torch.cuda.Event()
+            self.decode_done[k].record()
         # RunningScore's own policy: the int32 per-launch partial is folded into the int64 matrix lazily, before it
         # could overflow (every 2^30 scored pixels) and whenever the matrix is read
         if merge_now:
@@ -396,7 +427,7 @@ class SemanticRunner:
         else:
             self.merges += self.meter._pending + self.B * H * W >= (1 << 30)
             self.meter._note_pixels(self.B * H * W)
-        if ev: ev[3].record()
+        if ev: ev[4].record()
 
     def bytes_decode(self):
         c = self.cfg
@@ -422,17 +453,21 @@ def timed_steps(runner, steps, warmup, world, dist, sampler=None):
         runner.step(i)
     runner.meter.reset(); runner.merges = 0
     barrier()
-    n_ev = min(steps, 512)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_ev)]
+    # per-kernel events on a sample of the steps only: five timing events cost a step ~10 us of gaps between its kernels
+    # (tools/host_cost_probe.py), which at one step in `stride_ev` stays below 1 % of the elapsed time
+    n_ev = min(steps, 64)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(n_ev)]
     stride_ev = max(1, steps // n_ev)
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if sampler:
         sampler.sample_once(); sampler.start()
     start.record()
+    if runner.pipelined:
+        runner.gemm_stream.wait_event(start)                # nothing of the timed steps starts before `start`
     for i in range(steps):
         j = i // stride_ev
         runner.step(i, evs[j] if (i % stride_ev == 0 and j < n_ev) else None)
-    stop.record()
+    stop.record()                                           # after the last decode, which waited for the last contraction
     barrier()
     elapsed_ms = start.elapsed_time(stop)
     if world > 1:
@@ -441,19 +476,25 @@ def timed_steps(runner, steps, warmup, world, dist, sampler=None):
         elapsed_ms = float(t.item())
     used = [e for k, e in enumerate(evs) if k * stride_ev < steps]
     kern = {"contraction": float(np.mean([e[0].elapsed_time(e[1]) for e in used])),
-            "decode_score": float(np.mean([e[1].elapsed_time(e[2]) for e in used])),
-            "hist_merge": float(np.mean([e[2].elapsed_time(e[3]) for e in used]))}
+            "decode_score": float(np.mean([e[2].elapsed_time(e[3]) for e in used])),
+            "hist_merge": float(np.mean([e[3].elapsed_time(e[4]) for e in used]))}
     return elapsed_ms, kern
 
 
-def roofline_block(runner, kern, decode):
+def roofline_block(runner, kern, decode, alone=None):
+    """`kern`: per-kernel CUDA-event means inside the timed region (under the two-stream pipeline a kernel shares the GPU with
+    the other kernel's tail); `alone`: the same from the single-stream pass, where each kernel has the GPU to itself."""
     peak, peak_src = measured_peak_hbm()
     bd, bg = runner.bytes_decode(), runner.bytes_gemm()
     kname = "decode_cells_kernel" if runner.cells_path(decode) else ("decode_tiled_kernel" if decode != "generic" else "decode_generic_kernel")
     ach = bd / (kern["decode_score"] * 1e-3) / 1e9
     achg = bg / (kern["contraction"] * 1e-3) / 1e9
+    solo = None
+    if alone:
+        a_d, a_g = bd / (alone["decode_score"] * 1e-3) / 1e9, bg / (alone["contraction"] * 1e-3) / 1e9
+        solo = {"achieved": a_d, "frac": a_d / peak, "contraction": {"achieved": a_g, "frac": a_g / peak}}
     return {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": ncu_traffic(kname), "algorithmic_bytes_per_launch": bd, "peak_source": peak_src,
+            "traffic": ncu_traffic(kname), "algorithmic_bytes_per_launch": bd, "peak_source": peak_src, "kernel_alone": solo,
             "contraction": {"achieved": achg, "frac": achg / peak, "algorithmic_bytes_per_launch": bg, "traffic": ncu_traffic("contraction")},
             "step": {"achieved": (bd + bg) / ((kern["decode_score"] + kern["contraction"]) * 1e-3) / 1e9,
                      "frac": (bd + bg) / ((kern["decode_score"] + kern["contraction"]) * 1e-3) / 1e9 / peak}}
@@ -582,7 +623,7 @@ def bench_instance(cfg, device, steps, warmup, world=1, dist=None):
         dist.barrier()
     torch.cuda.synchronize()
     n_ev = min(steps, 256)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_ev)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(n_ev)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
@@ -725,7 +766,7 @@ def run_ours(args, cfg, rank, local, world):
         return
 
     # -------------------------------------------------------------------- semantic path
-    runner = SemanticRunner(cfg, device, 1000 * rank, token_mode(args), args.precision, args.decode)
+    runner = SemanticRunner(cfg, device, 1000 * rank, token_mode(args), args.precision, args.decode, pipelined=not args.serial)
     elapsed_ms, kern = timed_steps(runner, args.steps, args.warmup, world, dist, sampler)
     clocks = sampler.stop()
     merges = runner.merges
@@ -741,6 +782,14 @@ def run_ours(args, cfg, rank, local, world):
     relabel = ops.decode_score(runner.logits, (H, W), mode=_ffi.DECODE_GENERIC)
     label_mismatch = int((relabel != runner.labels).sum().item())
     del exact, relabel
+    serial = None
+    if runner.pipelined and not args.no_extras:
+        # the same steps on ONE stream (kernels alone on the GPU): what the two-stream pipeline is compared with
+        runner.pipelined = False
+        k = min(args.steps, 400)
+        ms1, kern1 = timed_steps(runner, k, 3, world, dist)
+        serial = {"ms_per_step": ms1 / k, "kernels_ms": kern1, "steps": k}
+        runner.pipelined = True
 
     e2e = e2e_semantic(args, cfg, runner, local, world, dist, numa) if args.e2e_steps > 0 else None
     strong = allred = None
@@ -758,12 +807,16 @@ def run_ours(args, cfg, rank, local, world):
                    "gt_dtype": "int64", "images_per_gpu_per_step": B, "parallelism": f"dp{world} (images sharded, one int64 all-reduce at the end)",
                    "contraction": {0: "fp32 FFMA", 1: "tcgen05 3xTF32", 2: "tcgen05 TF32 single pass"}[runner.flags & 3],
                    "decode": args.decode + (" (exact per-cell candidate pruning, decode_cells_kernel)" if runner.cells_path(args.decode) else ""),
-                   "l2_policy": f"{runner.n_sets} rotating input sets of {runner.tok_bytes / 1e6:.0f} MB tokens each (> 126 MB L2 between reuses)"},
+                   "l2_policy": f"{runner.n_sets} rotating input sets of {runner.tok_bytes / 1e6:.0f} MB tokens each (> 126 MB L2 between reuses)",
+                   "streams": ("2: the contraction of step i+1 is enqueued on its own stream and runs as the SMs of step i's decode drain "
+                               "(two logits buffers); kernels_ms are CUDA events on each kernel's stream inside the timed region")
+                              if runner.pipelined else "1"},
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": 2 * args.steps + merges,
         "kernels_ms": kern,
-        "roofline": roofline_block(runner, kern, args.decode),
+        "single_stream": serial,
+        "roofline": roofline_block(runner, kern, args.decode, serial["kernels_ms"] if serial else None),
         "strong": strong,
         "allreduce_us": allred,
         "check": {"mean_iou": float(scores["Mean IoU"]), "pixels_scored": total_px, "max_logit_err_vs_fp32_kernel": logit_err,

@@ -476,6 +476,28 @@ def test_compute_iou_drop_in(zb, golden):
         zb.compute_iou(np.zeros((2, 3)), np.zeros((3, 2)))
 
 
+def test_streaming_scorer_equals_batch_by_batch(zb):
+    """StreamingScorer (decode + scoring on its own stream) against decode_and_score batch by batch: same matrix, and
+    the caller's stream really is left free (the scoring of a batch is still pending when submit returns)."""
+    gen = torch.Generator().manual_seed(31)
+    Q, D, h, w, H, W = 21, 64, 14, 14, 112, 112
+    text = torch.nn.functional.normalize(torch.randn(Q, D, generator=gen), dim=-1).cuda()
+    batches = [(torch.randn(3, h, w, D, generator=gen).cuda(), torch.randint(0, Q, (3, H, W), generator=gen).cuda()) for _ in range(5)]
+    ref = zb.RunningScore(Q, device="cuda")
+    for tok, gt in batches:
+        zb.decode_and_score(text, tok, gt, (H, W), ref)
+    want = ref.confusion_matrix
+    meter = zb.RunningScore(Q, device="cuda")
+    scorer = zb.StreamingScorer(text, meter, (H, W))
+    for tok, gt in batches:
+        scorer.submit(tok, gt)
+    scores, _ = scorer.get_scores()
+    assert np.array_equal(meter.confusion_matrix, want)
+    assert scores["Mean IoU"] == ref.get_scores()[0]["Mean IoU"]
+    # the scoring stream is not the caller's
+    assert scorer._stream.cuda_stream != torch.cuda.current_stream().cuda_stream
+
+
 # --------------------------------------------------------------------------------- instance path
 def test_threshold_masks_bit_exact(zb):
     gen = torch.Generator().manual_seed(4)

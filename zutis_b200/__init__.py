@@ -12,7 +12,7 @@ from . import _ffi
 from ._ffi import ZutisBadArgument, ZutisError, ZutisUnsupported
 
 __all__ = [
-    "RunningScore", "compute_iou", "predict", "get_mask_proposals", "decode_and_score", "ZutisDecoder",
+    "RunningScore", "compute_iou", "predict", "get_mask_proposals", "decode_and_score", "ZutisDecoder", "StreamingScorer",
     "install", "shard_range", "ZutisError", "ZutisBadArgument", "ZutisUnsupported",
 ]
 
@@ -23,7 +23,7 @@ def __getattr__(name):
     lazy = {
         "RunningScore": "running_score", "compute_iou": "iou",
         "predict": "decode", "get_mask_proposals": "decode", "decode_and_score": "decode",
-        "ZutisDecoder": "decode", "install": "decode", "image_to_text_space": "decode",
+        "ZutisDecoder": "decode", "StreamingScorer": "decode", "install": "decode", "image_to_text_space": "decode",
         "shard_range": "distributed", "init_distributed": "distributed",
     }
     if name in lazy:

@@ -404,9 +404,11 @@ __global__ void __launch_bounds__(kCellWarpsMax * 32, 1) decode_cells_kernel(con
 #pragma unroll
                 for (int r = 0; r < 8; ++r) { best[r] = -INFINITY; win[r] = 0; }
                 const uint32_t val_m = val_base + (uint32_t)(cell * (cap + 1)) * 16u;
+                float4 v = lds128(nloop > 0 ? val_m : sent_addr);
 #pragma unroll 1
                 for (int j = 0; j < maxn; ++j) {
-                    const float4 v = lds128(j < nloop ? val_m + (uint32_t)j * 16u : sent_addr);
+                    // the next record is requested before this one is used
+                    const float4 nv = lds128(j + 1 < nloop ? val_m + (uint32_t)(j + 1) * 16u : sent_addr);
                     float t, u;
                     unpack2(fma2(LX0, pack2(v.x, v.y), mul2(LX1, pack2(v.z, v.w))), t, u);      // t = fma(lx0,A,lx1*B), u = fma(lx0,C,lx1*D)
                     const unsigned long long tt = pack2(t, t), uu = pack2(u, u);
@@ -417,6 +419,7 @@ __global__ void __launch_bounds__(kCellWarpsMax * 32, 1) decode_cells_kernel(con
                         if (v0 > best[2 * q]) { best[2 * q] = v0; win[2 * q] = j; }
                         if (v1 > best[2 * q + 1]) { best[2 * q + 1] = v1; win[2 * q + 1] = j; }
                     }
+                    v = nv;
                 }
                 const uint32_t ids_m = id_base + (uint32_t)(cell * (cap + 1)) * 2u;
                 int lab[8];
@@ -610,6 +613,7 @@ int launch_decode_cells(const DecodeParams& d, bool forced, int label_dtype, uns
     const bool staged = d.Q <= 128;
     // survivor slots per cell and warps per CTA: narrow Q keeps up to 32 warps resident, wide Q trades warps for longer lists
     int warps = staged ? kCellWarpsMax : 16;
+    if (const char* e = getenv("ZUTIS_EXP_DECODE_WARPS")) warps = atoi(e);
     p.cap = staged ? 40 : 96;
     if (p.cap > Qp) p.cap = Qp;
     p.tap_pitch_bytes = Qp * 4;

@@ -246,6 +246,10 @@ ZUTIS_API int zutis_image_layernorm_l2norm(float* x, int B, long pixels, int D, 
 ZUTIS_API int zutis_semantic_eval_host(const float* text, const float* tokens, const void* gt, int gt_dtype,
                                        int B, int Q, int D, int h, int w, int H, int W,
                                        long long* hist_host, int16_t* labels_host, int gemm_flags, int device);
+/* Bytes one call of zutis_semantic_eval_host moves host -> device.  Integer ground truth crosses PCIe in the narrowest
+ * type that leaves the confusion matrix unchanged (labels outside [0, Q) are ignored by running_score.py:11 and all map
+ * to one out-of-range sentinel): uint8 for Q <= 255, else int16; host threads narrow it while the tokens are copied. */
+ZUTIS_API size_t zutis_semantic_eval_host_h2d_bytes(int gt_dtype, int want_hist, int B, int Q, int D, int h, int w, int H, int W);
 
 #ifdef __cplusplus
 }

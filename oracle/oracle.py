@@ -261,8 +261,10 @@ def torch_image_to_text_space(tokens, proj, layer_norm: bool = True):
 
 
 def hard_nms(masks: np.ndarray, scores: np.ndarray, cats: np.ndarray,
-             nms_threshold: float = 0.3, score_floor: float = 0.001) -> List[Tuple[int, int, float]]:
-    """zutis.py:225-282 (nms_type="hard") -> list of (category, query index, score) kept.
+             nms_threshold: float = 0.3, score_floor: float = 0.001, nms_type: str = "hard",
+             sigma: float = 0.5) -> List[Tuple[int, int, float]]:
+    """zutis.py:225-282 -> list of (category, query index, score) kept; nms_type "hard" (the default of predict),
+    "linear" (score *= 1 - iou above the threshold) or "gaussian" (score *= exp(-iou^2 / sigma)), :261-266.
 
     Per category (0 = background skipped, iterated in ``set`` order like the reference):
     repeatedly keep the best-scoring candidate, drop candidates whose IoU with it exceeds
@@ -286,7 +288,13 @@ def hard_nms(masks: np.ndarray, scores: np.ndarray, cats: np.ndarray,
                 inter = np.logical_and(masks[i], masks[best]).sum()
                 union = np.logical_or(masks[i], masks[best]).sum()
                 iou = inter / (union + 1e-7)
-                s = s * (0 if iou > nms_threshold else 1)
+                if nms_type == "hard":
+                    weight = 0 if iou > nms_threshold else 1
+                elif nms_type == "linear":
+                    weight = (1 - iou) if iou > nms_threshold else 1
+                else:
+                    weight = np.exp(-(iou * iou) / sigma)
+                s = s * weight
                 if s > score_floor:
                     nxt.append(i); nxt_scores.append(s)
             cand, cand_scores = nxt, nxt_scores

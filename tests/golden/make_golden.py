@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 REF = "/root/reference"
-OUT = os.path.dirname(os.path.abspath(__file__))
+OUT = os.environ.get("ZUTIS_GOLDEN_OUT", os.path.dirname(os.path.abspath(__file__)))
 
 
 def install_stubs():
@@ -199,7 +199,7 @@ def main():
     mp = torch.sigmoid(3 * up)                                 # 5-D: the last layer is taken (:379-382)
     self_ns = SimpleNamespace(text_embeddings=t)
     self_ns.non_maximum_suppression = types.MethodType(ZUTIS.non_maximum_suppression, self_ns)
-    for tag, nms in (("hard", "hard"), ("none", None)):
+    for tag, nms in (("hard", "hard"), ("none", None), ("linear", "linear"), ("gaussian", "gaussian")):
         preds = ZUTIS.predict(self_ns, {"mask_proposals": mp, "patch_tokens": x}, "instance",
                               size=(70, 90), image_ids=[5, 6], nms_type=nms)
         ic[f"{tag}_category"] = np.array([p["category_id"] for p in preds], np.int64)

@@ -51,6 +51,18 @@ def test_argument_counts_match_header():
         assert n == len(args), f"{name}: header has {n} parameters, ctypes table has {len(args)}"
 
 
+def test_host_entry_h2d_bytes_accounts_for_narrowed_labels():
+    """int64 / int32 labels cross PCIe as uint8 (n <= 255) or int16; no histogram requested -> the caller's type."""
+    f = _ffi.lib().zutis_semantic_eval_host_h2d_bytes
+    B, Q, D, h, w, H, W = 4, 81, 512, 40, 40, 320, 320
+    fixed = Q * D * 4 + B * h * w * D * 4
+    assert f(_ffi.GT_I64, 1, B, Q, D, h, w, H, W) == fixed + B * H * W
+    assert f(_ffi.GT_I32, 1, B, Q, D, h, w, H, W) == fixed + B * H * W
+    assert f(_ffi.GT_U8, 1, B, Q, D, h, w, H, W) == fixed + B * H * W
+    assert f(_ffi.GT_I64, 1, B, 920, D, h, w, H, W) == 920 * D * 4 + B * h * w * D * 4 + 2 * B * H * W
+    assert f(_ffi.GT_I64, 0, B, Q, D, h, w, H, W) == fixed + 8 * B * H * W
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_fails_loudly_without_a_gpu():
     assert _ffi.lib().zutis_device_check(0) == _ffi.ERR_NO_DEVICE

@@ -515,14 +515,16 @@ def test_threshold_masks_bit_exact(zb):
 
 
 @pytest.mark.parametrize("fixture,prefix", [("instance_cases", ""), ("model_cfg1", "inst_")])
-@pytest.mark.parametrize("tag", ["hard", "none"])
+@pytest.mark.parametrize("tag", ["hard", "none", "linear", "gaussian"])
 def test_instance_predict_drop_in(zb, golden, fixture, prefix, tag):
     g = golden(fixture)
+    if f"{prefix}{tag}_score" not in g:
+        pytest.skip("soft-NMS outputs of the reference are stored for the synthetic proposals only")
     size = tuple(int(v) for v in g["size"]) if "size" in g else (224, 224)
     ids = [5, 6] if fixture == "instance_cases" else [11, 22]
     dec = zb.ZutisDecoder(dev(g["text"]))
     preds = dec.predict({"mask_proposals": dev(g["proposals"]), "patch_tokens": dev(g["tokens"])}, "instance",
-                        size=size, image_ids=ids, nms_type="hard" if tag == "hard" else None)
+                        size=size, image_ids=ids, nms_type=None if tag == "none" else tag)
     assert [p["category_id"] for p in preds] == g[f"{prefix}{tag}_category"].tolist()
     assert [p["image_id"] for p in preds] == g[f"{prefix}{tag}_image_id"].tolist()
     np.testing.assert_allclose(np.array([p["score"] for p in preds], np.float64).reshape(-1), g[f"{prefix}{tag}_score"], rtol=5e-6, atol=1e-9)
@@ -735,6 +737,32 @@ def test_host_entry_chunks_and_overlaps(zb):
     _ffi.call("zutis_semantic_eval_host", text.ctypes.data, tokens.ctypes.data, gt.ctypes.data, _ffi.GT_I32,
               B, Q, D, h, w, H, W, hist.ctypes.data, None, _ffi.GEMM_TF32X3, 0)          # accumulates into hist
     assert hist.sum() == 2 * B * (H - 3) * W
+
+
+@pytest.mark.parametrize("Q,gt_dtype", [(81, np.int64), (300, np.int64), (300, np.int32), (81, np.int16), (255, np.int64), (256, np.int64)])
+def test_host_entry_narrows_labels_exactly(zb, Q, gt_dtype):
+    """The host entry ships int64 / int32 / int16 labels as uint8 or int16 (csrc/host_eval.cu).  Everything the reference
+    ignores (negative, >= n, values whose low byte would look valid) must stay ignored; big batch = threaded path."""
+    from zutis_b200 import _ffi
+    B, D, h, w, H, W = (20 if Q == 81 else 3), 64, 12, 12, 96, 96
+    if Q == 81 and gt_dtype == np.int64:
+        H, W = 320, 320                                                # > 4 MB of labels: the worker threads run
+    gen = torch.Generator().manual_seed(Q)
+    text = torch.nn.functional.normalize(torch.randn(Q, D, generator=gen), dim=-1).numpy()
+    tokens = torch.nn.functional.normalize(torch.randn(B, h, w, D, generator=gen), dim=-1).numpy()
+    gt = torch.randint(0, Q, (B, H, W), generator=gen).numpy().astype(gt_dtype)
+    big = np.iinfo(gt_dtype).max
+    odd = [-1, -256, Q, Q + 1, 255, 256, 32767, big, big - 250, np.iinfo(gt_dtype).min]
+    if gt_dtype == np.int64:
+        odd += [2 ** 40 + 5, 2 ** 32, -(2 ** 33) + 7, 65536 + 3]
+    for k, v in enumerate(odd):
+        gt[:, k % H, (7 * k) % W::11] = v
+    code = {np.int64: _ffi.GT_I64, np.int32: _ffi.GT_I32, np.int16: _ffi.GT_I16}[gt_dtype]
+    hist = np.zeros((Q, Q), np.int64); labels = np.zeros((B, H, W), np.int16)
+    _ffi.call("zutis_semantic_eval_host", text.ctypes.data, tokens.ctypes.data, gt.ctypes.data, code,
+              B, Q, D, h, w, H, W, hist.ctypes.data, labels.ctypes.data, _ffi.GEMM_TF32X3, 0)
+    assert np.array_equal(hist, O.c_fast_hist(gt.astype(np.int64), labels.astype(np.int64), Q))
+    assert hist.sum() == int(((gt >= 0) & (gt < Q)).sum())
 
 
 def test_image_to_text_space_drop_in(zb, golden):

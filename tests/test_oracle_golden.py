@@ -129,7 +129,7 @@ def _instance_oracle(text, proposals, tokens, size, nms):
     out = []
     for b in range(masks.shape[0]):
         if nms:
-            kept = O.hard_nms(masks[b], conf[b], cat[b])
+            kept = O.hard_nms(masks[b], conf[b], cat[b], nms_type=nms)
         else:
             kept = [(int(c), i, float(s)) for i, (s, c) in enumerate(zip(conf[b], cat[b])) if c != 0 and masks[b, i].any()]
         out.append((b, kept, masks[b]))
@@ -137,11 +137,13 @@ def _instance_oracle(text, proposals, tokens, size, nms):
 
 
 @pytest.mark.parametrize("fixture,prefix", [("instance_cases", ""), ("model_cfg1", "inst_")])
-@pytest.mark.parametrize("tag", ["hard", "none"])
+@pytest.mark.parametrize("tag", ["hard", "none", "linear", "gaussian"])
 def test_instance_decode_matches_reference(golden, fixture, prefix, tag):
     g = golden(fixture)
+    if f"{prefix}{tag}_score" not in g:
+        pytest.skip("soft-NMS outputs of the reference are stored for the synthetic proposals only")
     size = tuple(int(v) for v in g["size"]) if "size" in g else (224, 224)
-    res = _instance_oracle(g["text"], g["proposals"], g["tokens"], size, tag == "hard")
+    res = _instance_oracle(g["text"], g["proposals"], g["tokens"], size, None if tag == "none" else tag)
     cats, scores, bits = [], [], []
     for b, kept, masks in res:
         for c, i, s in kept:
@@ -152,6 +154,24 @@ def test_instance_decode_matches_reference(golden, fixture, prefix, tag):
     assert len(bits) == len(ref_bits)
     if bits:
         assert np.array_equal(np.stack(bits), ref_bits)
+
+
+@pytest.mark.parametrize("nms_type", ["hard", "linear", "gaussian"])
+def test_host_nms_replay_matches_oracle(golden, nms_type):
+    """The product's host NMS (driven by intersection counts, used for soft NMS and for tied scores) against the oracle's
+    mask-based loop on the reference fixture's masks and scores."""
+    from zutis_b200.decode import _nms_keep
+    g = golden("instance_cases")
+    size = tuple(int(v) for v in g["size"])
+    conf, cat, _ = O.torch_instance_lowres(torch.from_numpy(g["text"]), torch.from_numpy(g["proposals"]), torch.from_numpy(g["tokens"]))
+    masks = O.c_decode_threshold(g["proposals"][:, -1], size, 0.5)
+    for b in range(masks.shape[0]):
+        flat = masks[b].reshape(masks.shape[1], -1).astype(np.int64)
+        inter = flat @ flat.T
+        got = _nms_keep(cat[b], conf[b], inter, nms_type)
+        want = O.hard_nms(masks[b], conf[b], cat[b], nms_type=nms_type)
+        assert [(int(c), q) for c, q, _ in got] == [(c, q) for c, q, _ in want]
+        assert [float(s) for _, _, s in got] == [s for _, _, s in want]
 
 
 def test_image_to_text_space_port_matches_reference(golden):

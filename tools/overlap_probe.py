@@ -1,4 +1,10 @@
-"""contraction(i+1) on one stream while decode(i) runs on another: does co-residency pay?"""
+"""contraction(i+1) on one stream while decode(i) runs on another, against the same launches on one stream.
+
+r02 measurements on cfg2 (us/step, serial -> two streams): product kernels 136.6 -> 125.8.  With temporary switches (not
+committed) that shrink both kernels until one CTA of each fits an SM together -- contraction rings of 3 pixel + 2 category
+slots (98 KB instead of 227 KB: 139.5 serial, i.e. the contraction barely needs its deep rings), decode CTAs of 8 / 10 / 12
+warps -- the co-resident pair ran at 172.6 / 156.5 / 143.9: the decode kernel needs all 20 warps x 96 registers of the SM
+to itself, and what it loses with fewer warps is more than the overlap returns."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np

@@ -67,6 +67,7 @@ SIGNATURES = {
     "zutis_image_norm_workspace_bytes": (_sz, [_i, _l, _i]),
     "zutis_image_layernorm_l2norm": (_i, [_vp, _i, _l, _i, _i, _f, _f, _vp, _sz, _vp]),
     "zutis_semantic_eval_host": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i]),
+    "zutis_semantic_eval_host_h2d_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _i, _i]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -613,7 +613,6 @@ int launch_decode_cells(const DecodeParams& d, bool forced, int label_dtype, uns
     const bool staged = d.Q <= 128;
     // survivor slots per cell and warps per CTA: narrow Q keeps up to 32 warps resident, wide Q trades warps for longer lists
     int warps = staged ? kCellWarpsMax : 16;
-    if (const char* e = getenv("ZUTIS_EXP_DECODE_WARPS")) warps = atoi(e);
     p.cap = staged ? 40 : 96;
     if (p.cap > Qp) p.cap = Qp;
     p.tap_pitch_bytes = Qp * 4;

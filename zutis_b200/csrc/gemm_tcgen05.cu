@@ -534,8 +534,6 @@ Plan make_plan(int M) {
     if (pl.sb > MAX_B) pl.sb = MAX_B;
     pl.sa = pl.sb >= 1 ? (budget - pl.sb * pl.b_slot_bytes) / A_TILE_BYTES : 0;
     if (pl.sa > MAX_A) pl.sa = MAX_A;
-    if (const char* e = getenv("ZUTIS_EXP_GEMM_SA")) pl.sa = atoi(e);
-    if (const char* e = getenv("ZUTIS_EXP_GEMM_SB")) pl.sb = atoi(e);
     pl.tmem_cols = 512;
     // TMEM: accumulators first, then 64 columns (A_hi | A_lo) per slot.  Double-buffer the accumulator when
     // at least 3 slots still fit beside it.

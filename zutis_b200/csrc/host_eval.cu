@@ -6,9 +6,20 @@
 // chunk i.  Streams, events, device scratch and the pinned read-back buffer live in a per-device context that is
 // created on first use and only ever grows: a call enqueues copies and kernels, nothing else (no stream creation, no
 // allocation, no synchronisation before the final read-back), which is what matters for small batches.
+//
+// Ground truth crosses PCIe in the narrowest type that keeps the confusion matrix unchanged: the kernels ignore every
+// label outside [0, n) (running_score.py:11), so an int64 / int32 label v becomes (0 <= v < n) ? v : sentinel in uint8
+// (n <= 255, sentinel 255) or int16 (sentinel -1).  A few host threads do that chunk by chunk into a pinned staging
+// buffer while the (8x larger) token copy of the same chunk is already on the wire; for the reference's int64 labels
+// this removes 17 % of the bytes of a step, and the copy engine is what bounds the call.
 #include "gemm.cuh"
 
+#include <sched.h>
+
+#include <atomic>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 using namespace zutis;
 
@@ -44,7 +55,46 @@ struct HostContext {
     Buffer text, hist;
     long long* h_hist = nullptr;     // pinned
     long h_hist_n = 0;
+    void* h_gt = nullptr;            // pinned staging of the narrowed ground truth
+    size_t h_gt_bytes = 0;
 };
+
+// bytes per ground-truth pixel after narrowing for n classes (0: leave the caller's type alone)
+int narrowed_gt_code(int gt_dtype, int n) {
+    const int have = gt_dtype_bytes(gt_dtype);
+    if (n <= 255 && have > 1) return ZUTIS_GT_U8;
+    if (n <= 32767 && have > 2) return ZUTIS_GT_I16;
+    return gt_dtype;
+}
+
+template <typename SRC, typename DST>
+void narrow_range(const SRC* src, DST* dst, size_t count, int n, DST sentinel) {
+    for (size_t i = 0; i < count; ++i) {
+        const SRC v = src[i];
+        dst[i] = (v >= 0 && v < (SRC)n) ? (DST)v : sentinel;
+    }
+}
+
+void narrow_labels(const void* src, int src_code, void* dst, int dst_code, size_t first, size_t count, int n) {
+    if (dst_code == ZUTIS_GT_U8) {
+        uint8_t* d = (uint8_t*)dst + first;
+        if (src_code == ZUTIS_GT_I64) narrow_range((const long long*)src + first, d, count, n, (uint8_t)255);
+        else if (src_code == ZUTIS_GT_I32) narrow_range((const int32_t*)src + first, d, count, n, (uint8_t)255);
+        else narrow_range((const int16_t*)src + first, d, count, n, (uint8_t)255);
+    } else {
+        int16_t* d = (int16_t*)dst + first;
+        if (src_code == ZUTIS_GT_I64) narrow_range((const long long*)src + first, d, count, n, (int16_t)-1);
+        else narrow_range((const int32_t*)src + first, d, count, n, (int16_t)-1);
+    }
+}
+
+int usable_cpus() {
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) != 0) return 1;
+    const int n = CPU_COUNT(&set);
+    return n > 0 ? n : 1;
+}
 
 HostContext g_ctx[64];
 
@@ -69,8 +119,13 @@ extern "C" int zutis_semantic_eval_host(const float* text, const float* tokens, 
     ZUTIS_REQUIRE(!hist_host || gt, "zutis_semantic_eval_host: hist requested without gt");
     ZUTIS_REQUIRE(B > 0 && Q > 0 && D > 0 && h > 0 && w > 0 && H > 0 && W > 0, "zutis_semantic_eval_host: bad shape");
     ZUTIS_REQUIRE(device >= 0 && device < 64, "zutis_semantic_eval_host: device %d out of range", device);
-    const int gt_bytes = gt_dtype_bytes(gt_dtype);
-    ZUTIS_REQUIRE(!gt || gt_bytes > 0, "zutis_semantic_eval_host: bad gt_dtype %d", gt_dtype);
+    const int src_gt_bytes = gt_dtype_bytes(gt_dtype);
+    ZUTIS_REQUIRE(!gt || src_gt_bytes > 0, "zutis_semantic_eval_host: bad gt_dtype %d", gt_dtype);
+    // ground truth is only read for the histogram; it crosses PCIe narrowed (see the header of this file)
+    const int src_gt_dtype = gt_dtype;
+    if (gt && hist_host) gt_dtype = narrowed_gt_code(gt_dtype, Q);
+    const bool narrow = gt && gt_dtype != src_gt_dtype;
+    const int gt_bytes = gt ? gt_dtype_bytes(gt_dtype) : 0;
     ZUTIS_CUDA(cudaSetDevice(device));
     int st = current_device_ok();
     if (st != ZUTIS_OK) return st;
@@ -106,6 +161,36 @@ extern "C" int zutis_semantic_eval_host(const float* text, const float* tokens, 
         ZUTIS_CUDA(cudaMallocHost((void**)&c.h_hist, (size_t)n2 * 8));
         c.h_hist_n = n2;
     }
+    if (narrow && c.h_gt_bytes < (size_t)B * HW * gt_bytes) {
+        if (c.h_gt) cudaFreeHost(c.h_gt);
+        c.h_gt = nullptr; c.h_gt_bytes = 0;
+        ZUTIS_CUDA(cudaMallocHost(&c.h_gt, (size_t)B * HW * gt_bytes));
+        c.h_gt_bytes = (size_t)B * HW * gt_bytes;
+    }
+    // narrowing runs ahead of the copies, chunk by chunk: worker t converts slice t of every chunk and bumps the chunk's
+    // counter; the enqueueing thread waits for a chunk's counter before it hands that chunk to the copy engine
+    const long n_chunks = (B + chunk - 1) / chunk;
+    int n_workers = 0;
+    std::vector<std::atomic<int>> narrowed(narrow ? n_chunks : 0);
+    std::vector<std::thread> workers;
+    if (narrow) {
+        for (auto& a : narrowed) a.store(0, std::memory_order_relaxed);
+        const size_t total = (size_t)B * HW;
+        n_workers = total * src_gt_bytes < (4u << 20) ? 0 : (usable_cpus() >= 8 ? 4 : (usable_cpus() >= 3 ? 2 : 1));
+        void* staging = c.h_gt;
+        auto work = [=, &narrowed](int t, int T) {
+            for (long k = 0; k < n_chunks; ++k) {
+                const size_t first = (size_t)k * chunk * HW;
+                const size_t count = (size_t)((B - k * chunk < chunk) ? (B - k * chunk) : chunk) * HW;
+                const size_t lo = first + count * t / T, hi = first + count * (t + 1) / T;
+                narrow_labels(gt, src_gt_dtype, staging, gt_dtype, lo, hi - lo, Q);
+                narrowed[k].fetch_add(1, std::memory_order_release);
+            }
+        };
+        if (n_workers == 0) { work(0, 1); n_workers = 1; }          // small batch: done before the first copy, no threads
+        else for (int t = 0; t < n_workers; ++t) workers.emplace_back(work, t, n_workers);
+    }
+    struct Joiner { std::vector<std::thread>& w; ~Joiner() { for (auto& t : w) if (t.joinable()) t.join(); } } joiner{workers};
 
     int rc = ZUTIS_OK;
     auto guard = [&](int s) { if (rc == ZUTIS_OK && s != ZUTIS_OK) rc = s; return rc == ZUTIS_OK; };
@@ -124,8 +209,14 @@ extern "C" int zutis_semantic_eval_host(const float* text, const float* tokens, 
         Lane& L = c.lanes[it % nlanes];
         const int nb = (int)((B - b0 < chunk) ? (B - b0) : chunk);
         guard(check_cuda(cudaMemcpyAsync(L.tokens.p, tokens + (size_t)b0 * hw * D, (size_t)nb * hw * D * 4, cudaMemcpyHostToDevice, L.stream), "H2D tokens"));
-        if (gt && rc == ZUTIS_OK)
-            guard(check_cuda(cudaMemcpyAsync(L.gt.p, (const char*)gt + (size_t)b0 * HW * gt_bytes, (size_t)nb * HW * gt_bytes, cudaMemcpyHostToDevice, L.stream), "H2D gt"));
+        if (gt && rc == ZUTIS_OK) {
+            const char* src = (const char*)gt;
+            if (narrow) {
+                while (narrowed[it].load(std::memory_order_acquire) < n_workers) std::this_thread::yield();
+                src = (const char*)c.h_gt;
+            }
+            guard(check_cuda(cudaMemcpyAsync(L.gt.p, src + (size_t)b0 * HW * gt_bytes, (size_t)nb * HW * gt_bytes, cudaMemcpyHostToDevice, L.stream), "H2D gt"));
+        }
         if (rc != ZUTIS_OK) break;
         const bool tensor_core = (gemm_flags & ZUTIS_GEMM_PRECISION_MASK) != ZUTIS_GEMM_FP32_SIMT;
         const int fl = gemm_flags | ((tensor_core && prepared[it % nlanes] && nb == chunk) ? ZUTIS_GEMM_A_PREPARED : 0);
@@ -157,4 +248,11 @@ extern "C" int zutis_semantic_eval_host(const float* text, const float* tokens, 
     if (hist_host && rc == ZUTIS_OK)
         for (long i = 0; i < n2; ++i) hist_host[i] += c.h_hist[i];
     return rc;
+}
+
+// Bytes the call above moves host -> device for one batch (text + tokens + ground truth as it crosses PCIe).
+extern "C" size_t zutis_semantic_eval_host_h2d_bytes(int gt_dtype, int want_hist, int B, int Q, int D, int h, int w, int H, int W) {
+    const int code = want_hist ? narrowed_gt_code(gt_dtype, Q) : gt_dtype;
+    const int gb = gt_dtype_bytes(code);
+    return (size_t)Q * D * 4 + (size_t)B * h * w * D * 4 + (size_t)B * H * W * (gb > 0 ? gb : 0);
 }

@@ -204,7 +204,8 @@ def _smooth_logits(B, Q, h, w, gen, contrast=1.0):
     return (contrast * torch.nn.functional.interpolate(coarse, size=(h, w), mode="bilinear", align_corners=True)).contiguous()
 
 
-@pytest.mark.parametrize("case", ["smooth", "smooth_noninteger", "x16", "x6", "iid", "ties", "nonfinite_mix", "wide", "wide_overflow", "hist_only", "uniform_regions", "near_ties"])
+@pytest.mark.parametrize("case", ["smooth", "smooth_noninteger", "x16", "x6", "iid", "ties", "nonfinite_mix", "wide", "wide_overflow", "hist_only", "uniform_regions", "near_ties",
+                                  "region_borders", "region_borders_wide", "region_borders_crowded"])
 def test_pruned_kernel_is_exact(zb, case):
     """The candidate-pruning (cell) kernel must give the generic kernel's labels and histogram bit for bit -- on coherent
     logits (where it prunes), on noise (where nearly everything survives and lists overflow), on exact ties and
@@ -247,6 +248,20 @@ def test_pruned_kernel_is_exact(zb, case):
         pick = torch.randint(0, 7, lo.shape, generator=gen)
         sign = torch.randint(0, 3, lo.shape, generator=gen).float() - 1.0  # ... perturbed by 0 or +-2^-24..2^-18 of the maximum
         lo = (lo + sign * scale[pick]).contiguous()
+    elif case.startswith("region_borders"):
+        # trained-model-like: every low-res pixel is confident about its region's category, regions of 3x3 pixels, the other
+        # categories are low noise.  On a cell across a border no single category dominates (the first attempt's list
+        # overflows); the average of the corner champions does (second attempt, virtual dominator).
+        Q = 300 if case.endswith("wide") else 81
+        B, h, w, H, W = 2, 12, 15, 96, 120
+        lo = 0.02 * torch.randn(B, Q, h, w, generator=gen)
+        region = torch.randint(0, Q, (B, 4, 5), generator=gen).repeat_interleave(3, 1).repeat_interleave(3, 2)
+        lo.scatter_add_(1, region[:, None], torch.ones(B, 1, h, w))
+        if case.endswith("crowded"):
+            # every other category sits within 2^-18 of 0.5, i.e. within the margin of k* on the far side of a border (k*
+            # is 1 on its side and ~0.5 on the other) but 0.25 below the virtual dominator
+            lo = 0.5 + 2.0 ** -18 * torch.randn(B, Q, h, w, generator=gen)
+            lo.scatter_(1, region[:, None], torch.ones(B, 1, h, w))
     elif case == "wide":
         B, Q, h, w, H, W = 1, 920, 7, 8, 56, 64; lo = _smooth_logits(B, Q, h, w, gen, 0.2)
     elif case == "wide_overflow":                                         # noise: ~390 of 600 categories survive, more than the 256 slots
@@ -259,6 +274,12 @@ def test_pruned_kernel_is_exact(zb, case):
     ref = zb.ops.decode_score(t, (H, W), gt=gt.cuda(), hist_partial=ref_part, mode=_ffi.DECODE_GENERIC)
     if not case.startswith("wide"):
         assert np.array_equal(ref.cpu().numpy().astype(np.int64), O.c_decode_semantic(lo.numpy(), (H, W)))
+    if case.startswith("region_borders"):                               # the case is what it claims: k* alone would overflow
+        cells = torch.stack([lo[:, :, :-1, :-1], lo[:, :, :-1, 1:], lo[:, :, 1:, :-1], lo[:, :, 1:, 1:]])     # 4,B,Q,h-1,w-1
+        kstar = cells.amin(0).argmax(1, keepdim=True)                                                           # B,1,h-1,w-1
+        K = torch.gather(cells, 2, kstar[None].expand(4, -1, -1, -1, -1))
+        survivors = (~((K - cells) >= K.abs().amax(0) * 2.0 ** -20).all(0)).sum(1)
+        assert (survivors > 40).float().mean() > 0.2
     for mode in (_ffi.DECODE_CELLS, _ffi.DECODE_AUTO):
         part = torch.zeros(Q * Q, dtype=torch.int32, device="cuda")
         got = zb.ops.decode_score(t, (H, W), gt=gt.cuda(), hist_partial=part, mode=mode, want_labels=want_labels)

@@ -30,6 +30,21 @@ def _survivors(A, B, C, D, k):
     return ~(lead >= margin)
 
 
+def _survivors_virtual(A, B, C, D):
+    """The second attempt of the kernel (cells whose first list overflows): dominator V = average of the four corner
+    champions, V_c = 0.25 * ((L_kA[c] + L_kB[c]) + (L_kC[c] + L_kD[c])) in fp32, margin 2^-19 * max|those 16 taps|."""
+    corners = (A, B, C, D)
+    champs = [int(np.argmax(X)) for X in corners]
+    V, big = [], np.float32(0)
+    for X in corners:
+        t = [np.float32(X[k]) for k in champs]
+        V.append(np.float32(0.25) * np.float32(np.float32(t[0] + t[1]) + np.float32(t[2] + t[3])))
+        big = max(big, np.float32(max(abs(v) for v in t)))
+    margin = np.float32(max(big * np.float32(2.0 ** -19), np.float32(1e-37)))
+    lead = np.minimum.reduce([(Vc - X).astype(np.float32) for Vc, X in zip(V, corners)])
+    return ~(lead >= margin)
+
+
 @pytest.mark.parametrize("case", ["smooth", "noise", "near_ties", "duplicates", "regions", "noninteger"])
 def test_pruning_rule_never_drops_the_winner(case):
     rng = np.random.default_rng(len(case) * 13 + 5)
@@ -58,7 +73,7 @@ def test_pruning_rule_never_drops_the_winner(case):
         lo[region, np.arange(h)[:, None], np.arange(w)[None, :]] += 1.0
     labels = O.c_decode_semantic(lo[None], (H, W))[0]
     ys, xs = _cells(h, H), _cells(w, W)
-    kept_total, singles = 0, 0
+    kept_total, singles, virtual_total = 0, 0, 0
     for cy in range(h):
         for cx in range(w):
             cy1, cx1 = min(cy + 1, h - 1), min(cx + 1, w - 1)
@@ -74,11 +89,18 @@ def test_pruning_rule_never_drops_the_winner(case):
             if keep.sum() == 1:
                 singles += 1
                 assert (cell == k).all(), (case, cy, cx, k, np.unique(cell))
+            # the virtual dominator (average of the corner champions) keeps every winner too, and never empties the list
+            keep_v = _survivors_virtual(A, B, C, D)
+            assert keep_v.any() and keep_v[np.unique(cell)].all(), (case, cy, cx, np.unique(cell), np.flatnonzero(keep_v))
+            if keep_v.sum() == 1:
+                assert (cell == np.flatnonzero(keep_v)[0]).all()
+            virtual_total += int(keep_v.sum())
             # which category dominates only changes how much is pruned, never whether a winner survives
             for other in (0, Q - 1, int(rng.integers(0, Q))):
                 assert _survivors(A, B, C, D, other)[np.unique(cell)].all(), (case, cy, cx, other)
     assert kept_total >= h * w                                          # at least the winner survives everywhere
     if case == "regions":
         assert singles > 0                                              # single-survivor cells are exercised
+        assert virtual_total < kept_total                               # across region borders the virtual dominator prunes more
     if case == "smooth":
         assert kept_total < 0.5 * Q * h * w                             # and the rule actually prunes

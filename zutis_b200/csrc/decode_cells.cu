@@ -250,12 +250,16 @@ __global__ void __launch_bounds__(kCellWarpsMax * 32, 1) decode_cells_kernel(con
             Kd = j == 0 ? d.x : (j == 1 ? d.y : (j == 2 ? d.z : d.w));
         }
         // 2^-20 * max|K|, never 0: k* must not dominate itself (its differences are exactly 0)
-        const float margin = fmaxf(fmaxf(fmaxf(fabsf(Ka), fabsf(Kb)), fmaxf(fabsf(Kc), fabsf(Kd))) * 9.5367431640625e-07f, 1e-37f);
-        const unsigned long long KA = pack2(Ka, Ka), KB = pack2(Kb, Kb), KC = pack2(Kc, Kc), KD = pack2(Kd, Kd);
+        float margin = fmaxf(fmaxf(fmaxf(fabsf(Ka), fabsf(Kb)), fmaxf(fabsf(Kc), fabsf(Kd))) * 9.5367431640625e-07f, 1e-37f);
+        unsigned long long KA = pack2(Ka, Ka), KB = pack2(Kb, Kb), KC = pack2(Kc, Kc), KD = pack2(Kd, Kd);
 
-        // pass 2: indices of the survivors, ascending, into the cell's list
+        // pass 2: indices of the survivors, ascending, into the cell's list.  Run a second time, with a different
+        // dominator, for cells whose list overflowed (see below).
+        int n;                                              // survivors of this lane's cell (same in its 8 lanes)
+#pragma unroll 1
+        for (int attempt = 0;; ++attempt) {
         unsigned long long acc = pack2(0.f, 0.f);          // sum of all differences: non-finite iff a tap is NaN / inf (or overflow)
-        int n = 0;                                          // survivors of this lane's cell so far (same in its 8 lanes)
+        n = 0;
 #pragma unroll
         for (int it = 0; it < iters; ++it) {
             const int c4 = it * kSlices + slice;
@@ -306,13 +310,75 @@ __global__ void __launch_bounds__(kCellWarpsMax * 32, 1) decode_cells_kernel(con
             sts_u16_if(k3, my_id + (uint32_t)min(pos, cap) * 2u, q0 + 3);
         }
         // non-finite anywhere in the cell: brute force with torch's NaN ordering
+        bool finite;
         {
             float sa, sb_;
             unpack2(acc, sa, sb_);
             float tot = __fadd_rn(sa, sb_);
 #pragma unroll
             for (int o = 1; o < kSlices; o <<= 1) tot = __fadd_rn(tot, __shfl_xor_sync(kFull, tot, o));
-            if (!(fabsf(tot) <= 3.402823466e38f)) n = cap + 1;
+            finite = fabsf(tot) <= 3.402823466e38f;
+            if (!finite) n = cap + 1;
+        }
+        // A list that overflows means k* does not dominate: typically a cell on the border of two regions, where one
+        // category leads on the left corners and another on the right ones, and everything in between survives both.
+        // Such a cell gets a second attempt with a VIRTUAL dominator, the average of the four corner champions
+        //     V_c = (L_kA[c] + L_kB[c] + L_kC[c] + L_kD[c]) / 4,   k_X = argmax_q L_q[X],
+        // whose interpolant is the average of four real interpolants and therefore never above their maximum: a
+        // category that stays m' = 2^-19 * max|the 16 taps| below V at all four corners stays below that maximum at
+        // every pixel.  (m' covers the roundings of the two interpolants, 2^-21 max|tap| as above, plus the
+        // 0.75 * 2^-22 max|tap| of computing V in fp32.)  Each corner champion is within reach of V at its own
+        // corner, so the list is never empty.
+        const bool again = attempt == 0 && finite && n > cap;
+        if (!__any_sync(kFull, again)) break;
+        {
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            int ix[4] = {0, 0, 0, 0};
+            for (int it = 0; it < iters; ++it) {
+                const int c4 = it * kSlices + slice;
+                if (c4 < nf4) {
+                    float4 t[4];
+                    if (STAGED) { t[0] = lds128(aA + it * 128); t[1] = lds128(aB + it * 128); t[2] = lds128(aC + it * 128); t[3] = lds128(aD + it * 128); }
+                    else { t[0] = __ldg(gA + it * kSlices); t[1] = __ldg(gB + it * kSlices); t[2] = __ldg(gC + it * kSlices); t[3] = __ldg(gD + it * kSlices); }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float e[4] = {t[c].x, t[c].y, t[c].z, t[c].w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (c4 * 4 + k < p.Q && e[k] > mx[c]) { mx[c] = e[k]; ix[c] = c4 * 4 + k; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int o = 1; o < kSlices; o <<= 1) {
+                    const float om = __shfl_xor_sync(kFull, mx[c], o);
+                    const int oi = __shfl_xor_sync(kFull, ix[c], o);
+                    if (om > mx[c] || (om == mx[c] && oi < ix[c])) { mx[c] = om; ix[c] = oi; }
+                }
+            const uint32_t corner[4] = {aA - (uint32_t)slice * 16u, aB - (uint32_t)slice * 16u, aC - (uint32_t)slice * 16u, aD - (uint32_t)slice * 16u};
+            const float* gcorner[4] = {reinterpret_cast<const float*>(gA - slice), reinterpret_cast<const float*>(gB - slice),
+                                       reinterpret_cast<const float*>(gC - slice), reinterpret_cast<const float*>(gD - slice)};
+            float V[4], big = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float t0, t1, t2, t3;
+                if (STAGED) {
+                    t0 = lds32(corner[c] + (uint32_t)ix[0] * 4u); t1 = lds32(corner[c] + (uint32_t)ix[1] * 4u);
+                    t2 = lds32(corner[c] + (uint32_t)ix[2] * 4u); t3 = lds32(corner[c] + (uint32_t)ix[3] * 4u);
+                } else {
+                    t0 = __ldg(gcorner[c] + ix[0]); t1 = __ldg(gcorner[c] + ix[1]); t2 = __ldg(gcorner[c] + ix[2]); t3 = __ldg(gcorner[c] + ix[3]);
+                }
+                V[c] = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(t0, t1), __fadd_rn(t2, t3)));
+                big = fmaxf(big, fmaxf(fmaxf(fabsf(t0), fabsf(t1)), fmaxf(fabsf(t2), fabsf(t3))));
+            }
+            if (again) {
+                KA = pack2(V[0], V[0]); KB = pack2(V[1], V[1]); KC = pack2(V[2], V[2]); KD = pack2(V[3], V[3]);
+                margin = fmaxf(big * 1.9073486328125e-06f, 1e-37f);
+            }
+        }
+        __syncwarp();
         }
         __syncwarp();
         // ---- gather, lane = list entry of the run: survivor j of cell c -> (A, C, B, D) next to its index

@@ -199,11 +199,11 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
 
 
-def ncu_traffic(kernel):
-    """dram bytes per launch from the committed ncu summary, if one exists (profiles/traffic.json)."""
+def ncu_traffic(kernel, workload):
+    """dram bytes per launch of `kernel` on `workload` from the committed ncu capture, if there is one (profiles/traffic.json)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(p)).get(kernel)
+        return json.load(open(p)).get(workload, {}).get(kernel)
     except Exception:
         return None
 
@@ -481,7 +481,7 @@ def timed_steps(runner, steps, warmup, world, dist, sampler=None):
     return elapsed_ms, kern
 
 
-def roofline_block(runner, kern, decode, alone=None, step_ms=None):
+def roofline_block(runner, kern, decode, alone=None, step_ms=None, workload=None):
     """Roofline of the dominant kernel (decode) and of the contraction.
 
     A launch duration is only the kernel's own when it has the GPU to itself.  Under the two-stream pipeline the CUDA events
@@ -496,12 +496,12 @@ def roofline_block(runner, kern, decode, alone=None, step_ms=None):
     achg = bg / (src["contraction"] * 1e-3) / 1e9
     t_step = step_ms if step_ms else (kern["decode_score"] + kern["contraction"])
     out = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-           "traffic": ncu_traffic(kname), "algorithmic_bytes_per_launch": bd, "peak_source": peak_src,
+           "traffic": ncu_traffic(kname, workload), "algorithmic_bytes_per_launch": bd, "peak_source": peak_src,
            "launch_ms": src["decode_score"],
            "timed": ("single-stream pass of the same steps (kernel alone on the GPU)" if alone else
                      "CUDA events on the kernel's stream inside the timed region"),
            "contraction": {"achieved": achg, "frac": achg / peak, "algorithmic_bytes_per_launch": bg, "launch_ms": src["contraction"],
-                           "traffic": ncu_traffic("contraction")},
+                           "traffic": ncu_traffic("contraction", workload)},
            "step": {"achieved": (bd + bg) / (t_step * 1e-3) / 1e9, "frac": (bd + bg) / (t_step * 1e-3) / 1e9 / peak, "ms": t_step}}
     if alone:
         out["event_spans_in_pipeline_ms"] = {"decode_score": kern["decode_score"], "contraction": kern["contraction"]}
@@ -652,7 +652,7 @@ def bench_instance(cfg, device, steps, warmup, world=1, dist=None):
     bytes_thr = B * (4 * Q * h * w + Q * H * ((W + 31) // 32) * 4)
     ach = bytes_thr / (kern["decode_threshold"] * 1e-3) / 1e9
     return ms, kern, {"bound": "hbm", "kernel": "threshold_tiled_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                      "traffic": ncu_traffic("threshold_tiled_kernel"), "algorithmic_bytes_per_launch": bytes_thr, "peak_source": src}
+                      "traffic": ncu_traffic("threshold_tiled_kernel", "cfg5"), "algorithmic_bytes_per_launch": bytes_thr, "peak_source": src}
 
 
 def other_configs(args, device, skip):
@@ -672,7 +672,7 @@ def other_configs(args, device, skip):
                 r = SemanticRunner(cfg, device, 300, False, args.precision, "auto", n_sets=3)
                 steps = 200 if name == "cfg1" else 40
                 ms, kern = timed_steps(r, steps, 3, 1, None)
-                roof = roofline_block(r, kern, "auto")
+                roof = roofline_block(r, kern, "auto", workload=name)
                 out[name] = {"value": cfg["B"] * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "kernels_ms": kern,
                              "roofline_frac": roof["frac"], "roofline_kernel": roof["kernel"], "contraction_frac": roof["contraction"]["frac"],
                              "steps": steps, "workload": cfg["desc"]}
@@ -832,7 +832,7 @@ def run_ours(args, cfg, rank, local, world):
         "kernels_ms": serial["kernels_ms"] if serial else kern,
         "single_stream": serial,
         "roofline": roofline_block(runner, kern, args.decode, serial["kernels_ms"] if serial else None,
-                                   elapsed_ms / args.steps if runner.pipelined else None),
+                                   elapsed_ms / args.steps if runner.pipelined else None, workload=args.workload),
         "strong": strong,
         "allreduce_us": allred,
         "check": {"mean_iou": float(scores["Mean IoU"]), "pixels_scored": total_px, "max_logit_err_vs_fp32_kernel": logit_err,

@@ -8,7 +8,7 @@
 # From zutis_b200/libzutis_b200.so: profiles/sass_<kernel>.txt (cuobjdump -sass of the hot kernels, mnemonics only) and
 #                   profiles/sass_mnemonics.txt             (counts of the Blackwell-specific mnemonics per kernel)
 # The reports themselves are made on the GPU box, e.g. (see /opt/skills/guides/B200_PROFILING.md):
-#   ncu --set full --clock-control none --import-source on -k regex:'cell_prune|cell_eval|gemm_tcgen05' -s 9 -c 3 \
+#   ncu --set full --clock-control none --import-source on -k regex:'decode_cells|gemm_tcgen05' -s 6 -c 2 \
 #       -o gpurun_out/<name> python bench.py --steps 4 --warmup 3 --e2e-steps 0 --no-cpu-baseline --no-extras
 #   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/<name>_launches.csv \
 #       python bench.py --steps 40 --warmup 3 --e2e-steps 0 --no-cpu-baseline --no-extras
@@ -41,14 +41,18 @@ PY
 done
 lib=zutis_b200/libzutis_b200.so
 : > profiles/sass_mnemonics.txt
-for k in gemm_tcgen05_kernel cell_prune_kernel cell_eval_kernel decode_cells_kernel decode_tiled_kernel threshold_tiled_kernel; do
+# kernel name -> substring of the mangled name that selects the instantiation (decode_cells: int64 ground truth, NI = 3,
+# the one the headline workload launches; the others: the first instantiation in the library)
+for spec in gemm_tcgen05_kernel:gemm_tcgen05_kernel decode_cells_kernel:decode_cells_kernelIxLi3 decode_tiled_kernel:decode_tiled_kernel \
+            threshold_tiled_kernel:threshold_tiled_kernel nms_hard_kernel:nms_hard_kernel; do
+    k=${spec%%:*}; pat=${spec##*:}
     out="profiles/sass_${k}.txt"
-    # the first instantiation of the kernel; mnemonics and operands only (no encodings)
-    cuobjdump -sass "$lib" | awk -v k="$k" '
+    # mnemonics and operands only (no encodings)
+    cuobjdump -sass "$lib" | awk -v k="$pat" '
         /Function :/ { if (on) exit; if (index($0, k) > 0) { on = 1; print } next }
         on && /^[[:space:]]+\/\*[0-9a-f]{4}\*\// { sub(/\/\* 0x[0-9a-f]+ \*\//, ""); sub(/[[:space:]]+$/, ""); print }' > "$out"
     {
-        echo "== $k ($(grep -c '/\*' "$out" || true) instructions in the first instantiation)"
+        echo "== $k ($(grep -c '/\*' "$out" || true) instructions; $(head -1 "$out" | sed -e 's/^[[:space:]]*//'))"
         for m in UTCHMMA UTCQMMA UTMALDG UTMASTG UBLKCP LDTM STTM UTCBAR SYNCS FFMA2 FMUL2 FADD2 FMNMX3 MATCH.ANY REDUX ATOMS RED LDGSTS; do
             c=$(grep -c "[[:space:]]$m" "$out" || true)
             [ "$c" != "0" ] && echo "   $m: $c"

@@ -319,7 +319,7 @@ def run_reference(args, cfg, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------- our arm
@@ -546,28 +546,34 @@ def strong_scaling(args, cfg, device, rank, world, dist):
         captured, graphs = False, []
         sys.stderr.write(f"bench.py: CUDA-graph capture of the strong-scaling step failed ({e}); timing eager launches\n")
         torch.cuda.synchronize()
-    steps = min(args.steps, 400)
+    steps = min(args.steps, 300)
     runner.meter.reset(); reduced.zero_()
     launch = (lambda i: graphs[i % len(graphs)].replay()) if captured else one
     for i in range(5):
         launch(i)
     runner.meter.reset()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        launch(i)
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    # three timed passes; the median is reported and all three are kept (one pass in a 2-GPU run was once 2x slower than
+    # its repeats on the same box: every step ends in a collective, so any hiccup of either rank lands in the pass)
+    passes = []
+    for _ in range(3):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            launch(i)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        passes.append(ms)
+    ms = sorted(passes)[1]
     # the N-rank reduced matrix of ONE pass over input set 0 must equal rank 0's single-GPU matrix over the same images
     runner.meter.reset()
     runner.step(0, merge_now=True)
@@ -581,7 +587,8 @@ def strong_scaling(args, cfg, device, rank, world, dist):
         equal = bool(torch.equal(solo.meter._hist, reduced))
         del solo
     return {"value": total * steps / (ms * 1e-3), "unit": UNIT, "images_total_per_step": total, "images_per_gpu": b - a, "steps": steps,
-            "ms_per_step": ms / steps, "cuda_graph": captured, "allreduce_inside_timed_region": world > 1,
+            "ms_per_step": ms / steps, "ms_per_step_passes": [m / steps for m in passes], "cuda_graph": captured,
+            "allreduce_inside_timed_region": world > 1,
             "reduced_matrix_equals_single_gpu": equal,
             "step": "contraction + decode_score + hist_merge + all_reduce(int64 Q x Q), one graph replay per step, max over ranks"}
 
@@ -775,7 +782,7 @@ def run_ours(args, cfg, rank, local, world):
                 "clocks": clocks, "e2e": None, "gpu_launches": 5 * args.steps, "kernels_ms": kern, "roofline": roof}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = time_cpu_baseline(cfg, 2, 3, False)
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     # -------------------------------------------------------------------- semantic path
@@ -856,11 +863,32 @@ def run_ours(args, cfg, rank, local, world):
             "what": "decode_and_score on the tensors the cpu_baseline leg timed, against oracle.torch_semantic_predict + OracleRunningScore"})
     if world == 1 and not args.no_extras:
         line["other_configs"] = other_configs(args, device, args.workload)
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1 whatever
+    NCCL_DEBUG_FILE says), so fd 1 is pointed at stderr for the whole run and the result line goes to the saved descriptor."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
     args = parse_args()
+    claim_stdout()
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -869,7 +897,6 @@ def main():
         run_reference(args, cfg, rank, world)
         return
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")        # NCCL's version banner goes to stdout; the contract is ONE JSON line
         from zutis_b200.distributed import init_distributed
         init_distributed("nccl")
     try:

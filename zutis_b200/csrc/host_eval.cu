@@ -205,10 +205,11 @@ extern "C" int zutis_semantic_eval_host(const float* text, const float* tokens, 
     for (int l = 1; l < nlanes; ++l) guard(check_cuda(cudaStreamWaitEvent(c.lanes[l].stream, c.text_ready, 0), "cudaStreamWaitEvent"));
 
     bool prepared[2] = {false, false};                 // the text operand's hi/lo split is made once per lane and call
-    for (long b0 = 0, it = 0; b0 < B && rc == ZUTIS_OK; b0 += chunk, ++it) {
+    // everything of chunk `it` after its token copy: labels in, contraction, decode + score, labels out
+    auto finish = [&](long it) {
         Lane& L = c.lanes[it % nlanes];
+        const long b0 = it * chunk;
         const int nb = (int)((B - b0 < chunk) ? (B - b0) : chunk);
-        guard(check_cuda(cudaMemcpyAsync(L.tokens.p, tokens + (size_t)b0 * hw * D, (size_t)nb * hw * D * 4, cudaMemcpyHostToDevice, L.stream), "H2D tokens"));
         if (gt && rc == ZUTIS_OK) {
             const char* src = (const char*)gt;
             if (narrow) {
@@ -217,19 +218,29 @@ extern "C" int zutis_semantic_eval_host(const float* text, const float* tokens, 
             }
             guard(check_cuda(cudaMemcpyAsync(L.gt.p, src + (size_t)b0 * HW * gt_bytes, (size_t)nb * HW * gt_bytes, cudaMemcpyHostToDevice, L.stream), "H2D gt"));
         }
-        if (rc != ZUTIS_OK) break;
+        if (rc != ZUTIS_OK) return;
         const bool tensor_core = (gemm_flags & ZUTIS_GEMM_PRECISION_MASK) != ZUTIS_GEMM_FP32_SIMT;
         const int fl = gemm_flags | ((tensor_core && prepared[it % nlanes] && nb == chunk) ? ZUTIS_GEMM_A_PREPARED : 0);
         guard(zutis_gemm_logits(d_text, D, 0, (const float*)L.tokens.p, D, hw * D, (float*)L.logits.p, 1, Qp, hw * Qp, Q, hw, D, nb, fl,
                                 L.gemm_ws.p, ws_bytes, L.stream));
-        if (rc != ZUTIS_OK) break;
+        if (rc != ZUTIS_OK) return;
         prepared[it % nlanes] = (nb == chunk);
         guard(zutis_decode_score_ws((const float*)L.logits.p, hw * Qp, 1, (long)w * Qp, Qp, nb, Q, h, w, H, W, L.gt.p, gt_dtype, HW,
                                     labels_host ? (int16_t*)L.labels.p : nullptr, hist_host ? (int32_t*)L.partial.p : nullptr, Q,
                                     ZUTIS_DECODE_AUTO | ZUTIS_DECODE_WORKSPACE_ZEROED, L.decode_ws.p, dws_bytes, L.stream));
         if (labels_host && rc == ZUTIS_OK)
             guard(check_cuda(cudaMemcpyAsync(labels_host + (size_t)b0 * HW, L.labels.p, (size_t)nb * HW * 2, cudaMemcpyDeviceToHost, L.stream), "D2H labels"));
+    };
+    // The token copy of chunk i goes to the copy engine BEFORE chunk i-1 is finished: if this thread has to wait for chunk
+    // i-1's narrowed labels, the wire is busy with chunk i's tokens meanwhile.
+    for (long it = 0; it < n_chunks && rc == ZUTIS_OK; ++it) {
+        Lane& L = c.lanes[it % nlanes];
+        const long b0 = it * chunk;
+        const int nb = (int)((B - b0 < chunk) ? (B - b0) : chunk);
+        guard(check_cuda(cudaMemcpyAsync(L.tokens.p, tokens + (size_t)b0 * hw * D, (size_t)nb * hw * D * 4, cudaMemcpyHostToDevice, L.stream), "H2D tokens"));
+        if (it > 0 && rc == ZUTIS_OK) finish(it - 1);
     }
+    if (rc == ZUTIS_OK) finish(n_chunks - 1);
     // lane 1 -> lane 0, then fold both lanes' int32 partials into one int64 matrix and bring it home
     for (int l = 1; l < nlanes && rc == ZUTIS_OK; ++l) {
         guard(check_cuda(cudaEventRecord(c.lanes[l].done, c.lanes[l].stream), "cudaEventRecord"));

@@ -33,7 +33,25 @@ bits, areas = ops.decode_threshold(probs, (120, 160), 0.5)
 ops.pairwise_mask_intersections(bits[0]); ops.unpack_mask_bits(bits[0], 160)
 ops.mask_rle(bits, 160); ops.mask_rle_strings(bits, 160, mask_ids=torch.tensor([3, 0, 5]))
 s, p, m = ops.instance_lowres_stats(probs, torch.randn(2, 15, 20, 512, device="cuda"), 0.5)
-ops.instance_categories(m, text, 5.0)
+cat_dev, prob_dev = ops.instance_categories(m, text, 5.0)
+inter = torch.stack([ops.pairwise_mask_intersections(bits[b]) for b in range(2)])
+ops.instance_nms_hard(inter, cat_dev.to(torch.int32).view(2, 100), torch.rand(2, 100, device="cuda"))      # device hard NMS
+# region borders: the first pruning attempt overflows, the second (virtual dominator) runs -- narrow and wide Q
+for Qb in (81, 300):
+    lob = 0.02 * torch.randn(2, Qb, 12, 15, device="cuda")
+    region = torch.randint(0, Qb, (2, 4, 5), device="cuda").repeat_interleave(3, 1).repeat_interleave(3, 2)
+    lob.scatter_add_(1, region[:, None], torch.ones(2, 1, 12, 15, device="cuda"))
+    Qp = (Qb + 3) & ~3
+    pb = torch.zeros(2, 12, 15, Qp, device="cuda"); pb[..., :Qb] = lob.permute(0, 2, 3, 1)
+    ops.decode_score(pb[..., :Qb].permute(0, 3, 1, 2), (96, 120), mode=_ffi.DECODE_CELLS)
+# host-buffer entry: chunked lanes + label narrowing threads
+B2 = 20
+th = torch.nn.functional.normalize(torch.randn(B2, 40, 40, 512), dim=-1).numpy(); gh = np.random.randint(0, 81, (B2, 320, 320)).astype(np.int64)
+hist = np.zeros((81, 81), np.int64)
+_ffi.call("zutis_semantic_eval_host", text.cpu().numpy().ctypes.data, th.ctypes.data, gh.ctypes.data, _ffi.GT_I64, B2, 81, 512, 40, 40, 320, 320,
+          hist.ctypes.data, None, _ffi.GEMM_TF32X3, 0)
+scorer = zutis_b200.StreamingScorer(text, zutis_b200.RunningScore(81), (224, 224))
+scorer.submit(tokens, gt); scorer.submit(tokens, gt); scorer.get_scores()
 ops.upsample_bilinear(lo2, (50, 60))
 torch.cuda.synchronize()
 print("sanitize probe done", float(meter.get_scores()[0]["Mean IoU"]))

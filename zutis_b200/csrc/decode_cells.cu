@@ -303,11 +303,11 @@ __global__ void __launch_bounds__(kCellWarpsMax * 32, 1) decode_cells_kernel(con
             }
             int pos = n + incl - mine;
             n += __shfl_sync(kFull, incl, kSlices - 1, kSlices);
-            // slots beyond the capacity collapse onto the spare slot [cap]; such a cell is evaluated by brute force
-            sts_u16_if(k0, my_id + (uint32_t)min(pos, cap) * 2u, q0); pos += k0;
-            sts_u16_if(k1, my_id + (uint32_t)min(pos, cap) * 2u, q0 + 1); pos += k1;
-            sts_u16_if(k2, my_id + (uint32_t)min(pos, cap) * 2u, q0 + 2); pos += k2;
-            sts_u16_if(k3, my_id + (uint32_t)min(pos, cap) * 2u, q0 + 3);
+            // entries beyond the capacity are not stored; such a cell is evaluated by brute force (n > cap)
+            sts_u16_if(k0 && pos < cap, my_id + (uint32_t)pos * 2u, q0); pos += k0;
+            sts_u16_if(k1 && pos < cap, my_id + (uint32_t)pos * 2u, q0 + 1); pos += k1;
+            sts_u16_if(k2 && pos < cap, my_id + (uint32_t)pos * 2u, q0 + 2); pos += k2;
+            sts_u16_if(k3 && pos < cap, my_id + (uint32_t)pos * 2u, q0 + 3);
         }
         // non-finite anywhere in the cell: brute force with torch's NaN ordering
         bool finite;

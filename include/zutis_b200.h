@@ -141,6 +141,13 @@ ZUTIS_API int zutis_score_labels(const void* gt, int gt_dtype, const void* pred,
 ZUTIS_API int zutis_hist_merge(int32_t* partials, int n_partials, long long* hist_i64, long n2,
                                int clear_partials, void* stream);
 
+/* Multi-GPU sum of the per-GPU matrices: ncclAllReduce(sum, int64, n2) in place on `stream` over
+ * the caller's communicator (an ncclComm_t passed as void*).  The library does not link NCCL; it takes ncclAllReduce from
+ * the NCCL already loaded in the process, i.e. the one the communicator belongs to.  Integer sums make the result
+ * bit-identical for any number of GPUs.  (Python callers without a raw communicator use RunningScore.all_reduce(), which
+ * goes through torch.distributed.) */
+ZUTIS_API int zutis_allreduce_hist(long long* hist_i64, long n2, void* nccl_comm, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * return_logits=True (networks/zutis.py:369-370): the one mode where full-resolution fp32 logits
  * are materialised on request.  out is [B,Q,H,W] contiguous.

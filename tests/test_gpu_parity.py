@@ -5,6 +5,8 @@ Bars (BASELINE.json north_star): integer work (labels for identical logits, conf
 bit-exact; low-res logits within 1e-5 of max|logit| (fp32-grade paths) or 2e-2 (bf16); label
 agreement with the reference path >= 99.99 % with disagreements only at fp ties; mIoU within 1e-4.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -784,6 +786,37 @@ def test_host_entry_narrows_labels_exactly(zb, Q, gt_dtype):
               B, Q, D, h, w, H, W, hist.ctypes.data, labels.ctypes.data, _ffi.GEMM_TF32X3, 0)
     assert np.array_equal(hist, O.c_fast_hist(gt.astype(np.int64), labels.astype(np.int64), Q))
     assert hist.sum() == int(((gt >= 0) & (gt < Q)).sum())
+
+
+def test_allreduce_hist_over_a_raw_nccl_communicator(zb):
+    """zutis_allreduce_hist: the int64 matrix summed in place over an ncclComm_t made with NCCL's own C API.
+    One GPU: a communicator of size 1 (the sum is the matrix itself; checks symbol resolution and the call).  Two or more
+    GPUs: tools/nccl_abi_probe.py under torchrun, every rank compares with the gathered per-rank matrices."""
+    import ctypes, subprocess, sys
+    nccl = ctypes.CDLL("libnccl.so.2")
+
+    class UniqueId(ctypes.Structure):
+        _fields_ = [("internal", ctypes.c_char * 128)]
+
+    uid = UniqueId()
+    assert nccl.ncclGetUniqueId(ctypes.byref(uid)) == 0
+    comm = ctypes.c_void_p()
+    nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, UniqueId, ctypes.c_int]
+    assert nccl.ncclCommInitRank(ctypes.byref(comm), 1, uid, 0) == 0
+    meter = zb.RunningScore(21, device="cuda")
+    gen = torch.Generator().manual_seed(8)
+    meter.update(torch.randint(0, 21, (2, 40, 40), generator=gen).cuda(), torch.randint(0, 21, (2, 40, 40), generator=gen).cuda())
+    before = meter.counts().clone()
+    meter.all_reduce(nccl_comm=comm.value)
+    torch.cuda.synchronize()
+    assert torch.equal(meter.counts(), before) and int(before.sum()) == 2 * 40 * 40
+    nccl.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+    nccl.ncclCommDestroy(comm)
+    if torch.cuda.device_count() >= 2:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                            "--master-port", "29547", os.path.join(root, "tools", "nccl_abi_probe.py")], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_image_to_text_space_drop_in(zb, golden):

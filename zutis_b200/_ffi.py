@@ -53,6 +53,7 @@ SIGNATURES = {
     "zutis_decode_score_ws": (_i, [_vp, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _vp, _i, _l, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "zutis_score_labels": (_i, [_vp, _i, _vp, _i, _l, _vp, _i, _vp]),
     "zutis_hist_merge": (_i, [_vp, _i, _vp, _l, _i, _vp]),
+    "zutis_allreduce_hist": (_i, [_vp, _l, _vp, _vp]),
     "zutis_upsample_bilinear": (_i, [_vp, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "zutis_decode_threshold": (_i, [_vp, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "zutis_unpack_mask_bits": (_i, [_vp, _l, _i, _i, _vp, _vp]),

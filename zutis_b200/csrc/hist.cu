@@ -5,6 +5,8 @@
 //                         (the "+=" of running_score.py:20) and clears the partials for reuse.
 #include "common.cuh"
 
+#include <mutex>
+
 namespace zutis {
 
 __global__ void __launch_bounds__(256) score_labels_kernel(const void* gt, int gt_dtype, const void* pred, int pred_dtype,
@@ -91,4 +93,38 @@ extern "C" int zutis_hist_merge(int32_t* partials, int n_partials, long long* hi
     if (blocks > cap) blocks = cap;
     hist_merge_kernel<<<(unsigned)blocks, 256, 0, stream>>>(partials, n_partials, hist_i64, n2, clear_partials);
     return check_launch("hist_merge_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------- multi-GPU sum
+// One ncclAllReduce(sum, int64, n^2) over the caller's communicator.  The library does not link
+// NCCL: the symbol is taken from the NCCL the host process has already loaded (torch's, or the host application's own), so the
+// communicator and the library always belong to the same NCCL build.
+#include <dlfcn.h>
+
+namespace {
+typedef int (*NcclAllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+NcclAllReduceFn resolve_nccl_allreduce() {
+    static NcclAllReduceFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = dlsym(RTLD_DEFAULT, "ncclAllReduce");
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            if (sym) break;
+            if (void* h = dlopen(name, RTLD_NOW | RTLD_NOLOAD)) sym = dlsym(h, "ncclAllReduce");   // already loaded (RTLD_LOCAL)
+        }
+        fn = reinterpret_cast<NcclAllReduceFn>(sym);
+    });
+    return fn;
+}
+}  // namespace
+
+extern "C" int zutis_allreduce_hist(long long* hist_i64, long n2, void* nccl_comm, void* stream) {
+    ZUTIS_REQUIRE(hist_i64 && nccl_comm, "zutis_allreduce_hist: NULL pointer");
+    ZUTIS_REQUIRE(n2 > 0, "zutis_allreduce_hist: n2=%ld", n2);
+    NcclAllReduceFn fn = resolve_nccl_allreduce();
+    if (!fn) return fail(ZUTIS_ERR_UNSUPPORTED, "zutis_allreduce_hist: no NCCL in this process (the communicator's library must be loaded first)");
+    const int nccl_int64 = 4, nccl_sum = 0;                      // ncclDataType_t / ncclRedOp_t values of nccl.h (stable since NCCL 2.0)
+    const int rc = fn(hist_i64, hist_i64, (size_t)n2, nccl_int64, nccl_sum, nccl_comm, (cudaStream_t)stream);
+    if (rc != 0) return fail(ZUTIS_ERR_CUDA, "zutis_allreduce_hist: ncclAllReduce returned ncclResult_t %d", rc);
+    return ZUTIS_OK;
 }

@@ -109,10 +109,16 @@ class RunningScore(object):
         self._note_pixels(gt.numel())
         return labels
 
-    def all_reduce(self, group=None) -> None:
-        """Sum the per-GPU matrices over the process group (one int64 all-reduce of n^2 counts)."""
-        import torch.distributed as dist
+    def all_reduce(self, group=None, nccl_comm: Optional[int] = None) -> None:
+        """Sum the per-GPU matrices (one int64 all-reduce of n^2 counts): over the torch.distributed process group, or --
+        for hosts that own a raw NCCL communicator -- over ``nccl_comm`` (the ncclComm_t as an integer) through the C ABI."""
         self._merge()
+        if nccl_comm is not None:
+            with torch.cuda.device(self.device):
+                ops.F.call("zutis_allreduce_hist", self._hist.data_ptr(), self._hist.numel(), nccl_comm,
+                       torch.cuda.current_stream(self.device).cuda_stream)
+            return
+        import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self._hist, op=dist.ReduceOp.SUM, group=group)
 

@@ -508,9 +508,11 @@ def roofline_block(runner, kern, decode, alone=None, step_ms=None, workload=None
     return out
 
 
-def strong_scaling(args, cfg, device, rank, world, dist):
+def strong_scaling(args, cfg, device, rank, world, dist, peer=None):
     """BASELINE's 'batch 64 on 8xB200': the config's B images in TOTAL, a contiguous shard per GPU, one step = contraction +
-    decode + merge + all-reduce of the int64 matrix, captured in one CUDA graph and timed with the all-reduce inside."""
+    decode + merge + all-reduce of the int64 matrix, captured in one CUDA graph and timed with the all-reduce inside.
+    peer: a zutis_b200.distributed.PeerReducer -> the all-reduce is the library's own kernel over NVLink peer memory,
+    otherwise NCCL through torch.distributed."""
     import torch
     from zutis_b200.distributed import shard_range
     total = cfg["B"]
@@ -521,11 +523,16 @@ def strong_scaling(args, cfg, device, rank, world, dist):
     Q = cfg["Q"]
     reduced = torch.zeros(Q * Q, dtype=torch.int64, device=device)
 
+    use_peer = peer is not None and world > 1 and Q * Q <= peer.max_elements
+
     def one(i):
         runner.step(i, merge_now=True)
-        reduced.copy_(runner.meter._hist)
-        if world > 1:
-            dist.all_reduce(reduced, op=dist.ReduceOp.SUM)
+        if use_peer:
+            peer.all_reduce(runner.meter._hist, out=reduced)
+        else:
+            reduced.copy_(runner.meter._hist)
+            if world > 1:
+                dist.all_reduce(reduced, op=dist.ReduceOp.SUM)
 
     for i in range(4):
         one(i)
@@ -577,9 +584,12 @@ def strong_scaling(args, cfg, device, rank, world, dist):
     # the N-rank reduced matrix of ONE pass over input set 0 must equal rank 0's single-GPU matrix over the same images
     runner.meter.reset()
     runner.step(0, merge_now=True)
-    reduced.copy_(runner.meter._hist)
-    if world > 1:
-        dist.all_reduce(reduced, op=dist.ReduceOp.SUM)
+    if use_peer:
+        peer.all_reduce(runner.meter._hist, out=reduced)
+    else:
+        reduced.copy_(runner.meter._hist)
+        if world > 1:
+            dist.all_reduce(reduced, op=dist.ReduceOp.SUM)
     equal = None
     if rank == 0:
         solo = SemanticRunner(cfg, device, 77, token_mode(args), args.precision, args.decode, n_sets=1)
@@ -590,12 +600,27 @@ def strong_scaling(args, cfg, device, rank, world, dist):
             "ms_per_step": ms / steps, "ms_per_step_passes": [m / steps for m in passes], "cuda_graph": captured,
             "allreduce_inside_timed_region": world > 1,
             "reduced_matrix_equals_single_gpu": equal,
+            "allreduce": ("zutis_allreduce_hist_p2p (own kernel over NVLink peer memory)" if use_peer else
+                          ("NCCL via torch.distributed" if world > 1 else "none (one GPU)")),
             "step": "contraction + decode_score + hist_merge + all_reduce(int64 Q x Q), one graph replay per step, max over ranks"}
 
 
-def allreduce_timing(device, world, dist):
+def allreduce_timing(device, world, dist, peer=None):
     import torch
     out = {}
+    if peer is not None:
+        buf = torch.ones(81 * 81, dtype=torch.int64, device=device); res = torch.empty_like(buf)
+        for _ in range(20):
+            peer.all_reduce(buf, out=res)
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(200):
+            peer.all_reduce(buf, out=res)
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e3 / 200], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["q81_peer_memory"] = float(t.item())
     for Q in (81, 920):
         buf = torch.ones(Q * Q, dtype=torch.int64, device=device)
         for _ in range(20):
@@ -609,7 +634,8 @@ def allreduce_timing(device, world, dist):
         t = torch.tensor([e0.elapsed_time(e1) * 1e3 / 200], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         out[f"q{Q}"] = float(t.item())
-    out["what"] = "NCCL all_reduce(SUM) of the int64 Q x Q confusion matrix alone, back to back, us per call, max over ranks"
+    out["what"] = ("all-reduce(SUM) of the int64 Q x Q confusion matrix alone, back to back, us per call, max over ranks: q81 / q920 "
+                   "through NCCL, q81_peer_memory through zutis_allreduce_hist_p2p")
     return out
 
 
@@ -814,9 +840,21 @@ def run_ours(args, cfg, rank, local, world):
     e2e = e2e_semantic(args, cfg, runner, local, world, dist, numa) if args.e2e_steps > 0 else None
     strong = allred = None
     if not args.no_extras:
-        strong = strong_scaling(args, cfg, device, rank, world, dist)
+        peer = None
         if world > 1:
-            allred = allreduce_timing(device, world, dist)
+            try:
+                from zutis_b200.distributed import PeerReducer
+                peer = PeerReducer(max_elements=128 * 128)
+            except Exception as e:                          # no CUDA IPC between the ranks (not one node, restricted container)
+                sys.stderr.write(f"bench.py: peer-memory all-reduce unavailable ({e}); NCCL only\n")
+        strong = strong_scaling(args, cfg, device, rank, world, dist, peer)
+        if world > 1:
+            if peer is not None:
+                strong["nccl"] = {k: v for k, v in strong_scaling(args, cfg, device, rank, world, dist, None).items()
+                                  if k in ("value", "ms_per_step", "ms_per_step_passes", "reduced_matrix_equals_single_gpu")}
+            allred = allreduce_timing(device, world, dist, peer)
+            if peer is not None:
+                peer.close()
     if rank != 0:
         return
     line = {

@@ -148,6 +148,19 @@ ZUTIS_API int zutis_hist_merge(int32_t* partials, int n_partials, long long* his
  * goes through torch.distributed.) */
 ZUTIS_API int zutis_allreduce_hist(long long* hist_i64, long n2, void* nccl_comm, void* stream);
 
+/* The same sum over NVLink peer memory, for small matrices (csrc/p2p_reduce.cu): every rank stages its matrix in a buffer
+ * its peers have mapped through CUDA IPC, and one kernel per rank signals, waits, sums all ranks' matrices with peer loads
+ * and signals again.  52 KB (Q = 81): ~8-10 us against 18-30 us for the library all-reduce.  One process per GPU of one node.
+ *   zutis_p2p_create   allocates this rank's block for matrices of up to max_n2 elements and returns its 64-byte IPC handle;
+ *   zutis_p2p_connect  takes all ranks' handles (world x 64 bytes, rank order; exchange them however the host likes);
+ *   zutis_allreduce_hist_p2p  out[i] = sum_r hist_r[i] on `stream` (out may be hist); every rank must make the same calls;
+ *                      the epoch of the handshake lives on the device, so the launch can be captured in a CUDA graph;
+ *   zutis_p2p_destroy  unmaps and frees. */
+ZUTIS_API int zutis_p2p_create(int world, int rank, long max_n2, unsigned char* ipc_handle_out, int* ctx_out);
+ZUTIS_API int zutis_p2p_connect(int ctx, const unsigned char* handles);
+ZUTIS_API int zutis_allreduce_hist_p2p(int ctx, const long long* hist, long n2, long long* out, void* stream);
+ZUTIS_API int zutis_p2p_destroy(int ctx);
+
 /* ---------------------------------------------------------------------------------------------
  * return_logits=True (networks/zutis.py:369-370): the one mode where full-resolution fp32 logits
  * are materialised on request.  out is [B,Q,H,W] contiguous.

@@ -819,6 +819,36 @@ def test_allreduce_hist_over_a_raw_nccl_communicator(zb):
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_peer_memory_allreduce(zb):
+    """zutis_allreduce_hist_p2p (csrc/p2p_reduce.cu).  One GPU: a context of world size 1 through the raw C ABI (staging,
+    handshake with itself, sum, epochs across repeated calls, in place and out of place).  Two or more GPUs:
+    tools/p2p_reduce_probe.py under torchrun compares with NCCL on every rank, eagerly and as a replayed CUDA graph."""
+    import ctypes as C, subprocess, sys
+    from zutis_b200 import _ffi
+    handle = (C.c_ubyte * 64)(); ctx = C.c_int(-1)
+    _ffi.call("zutis_p2p_create", 1, 0, 81 * 81, C.addressof(handle), C.addressof(ctx))
+    _ffi.call("zutis_p2p_connect", ctx.value, C.addressof(handle))
+    gen = torch.Generator().manual_seed(12)
+    stream = torch.cuda.current_stream().cuda_stream
+    for rep in range(5):
+        hist = torch.randint(0, 1 << 50, (81 * 81,), generator=gen).cuda()
+        out = torch.zeros_like(hist)
+        _ffi.call("zutis_allreduce_hist_p2p", ctx.value, hist.data_ptr(), hist.numel(), out.data_ptr(), stream)
+        assert torch.equal(out, hist)
+        keep = hist.clone()
+        _ffi.call("zutis_allreduce_hist_p2p", ctx.value, hist.data_ptr(), 21 * 21, hist.data_ptr(), stream)      # in place, smaller
+        assert torch.equal(hist, keep)
+    with pytest.raises(zb.ZutisBadArgument):
+        _ffi.call("zutis_allreduce_hist_p2p", ctx.value, hist.data_ptr(), 2 * 81 * 81, hist.data_ptr(), stream)     # does not fit the context
+    torch.cuda.synchronize()
+    _ffi.call("zutis_p2p_destroy", ctx.value)
+    if torch.cuda.device_count() >= 2:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                            "--master-port", "29549", os.path.join(root, "tools", "p2p_reduce_probe.py")], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_image_to_text_space_drop_in(zb, golden):
     """projection + joint layer norm + per-pixel L2 norm (zutis.py:319-322)."""
     g = golden("text_space")

@@ -54,6 +54,10 @@ SIGNATURES = {
     "zutis_score_labels": (_i, [_vp, _i, _vp, _i, _l, _vp, _i, _vp]),
     "zutis_hist_merge": (_i, [_vp, _i, _vp, _l, _i, _vp]),
     "zutis_allreduce_hist": (_i, [_vp, _l, _vp, _vp]),
+    "zutis_p2p_create": (_i, [_i, _i, _l, _vp, _vp]),
+    "zutis_p2p_connect": (_i, [_i, _vp]),
+    "zutis_allreduce_hist_p2p": (_i, [_i, _vp, _l, _vp, _vp]),
+    "zutis_p2p_destroy": (_i, [_i]),
     "zutis_upsample_bilinear": (_i, [_vp, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "zutis_decode_threshold": (_i, [_vp, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "zutis_unpack_mask_bits": (_i, [_vp, _l, _i, _i, _vp, _vp]),

@@ -109,10 +109,14 @@ class RunningScore(object):
         self._note_pixels(gt.numel())
         return labels
 
-    def all_reduce(self, group=None, nccl_comm: Optional[int] = None) -> None:
-        """Sum the per-GPU matrices (one int64 all-reduce of n^2 counts): over the torch.distributed process group, or --
-        for hosts that own a raw NCCL communicator -- over ``nccl_comm`` (the ncclComm_t as an integer) through the C ABI."""
+    def all_reduce(self, group=None, nccl_comm: Optional[int] = None, peer=None) -> None:
+        """Sum the per-GPU matrices (one int64 all-reduce of n^2 counts): over the torch.distributed process group; for
+        hosts that own a raw NCCL communicator over ``nccl_comm`` (the ncclComm_t as an integer) through the C ABI; or over
+        NVLink peer memory with a ``distributed.PeerReducer`` (one node, small matrices: a third of NCCL's latency)."""
         self._merge()
+        if peer is not None and self._hist.numel() <= peer.max_elements:
+            peer.all_reduce(self._hist)
+            return
         if nccl_comm is not None:
             with torch.cuda.device(self.device):
                 ops.F.call("zutis_allreduce_hist", self._hist.data_ptr(), self._hist.numel(), nccl_comm,

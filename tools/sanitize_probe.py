@@ -50,6 +50,16 @@ th = torch.nn.functional.normalize(torch.randn(B2, 40, 40, 512), dim=-1).numpy()
 hist = np.zeros((81, 81), np.int64)
 _ffi.call("zutis_semantic_eval_host", text.cpu().numpy().ctypes.data, th.ctypes.data, gh.ctypes.data, _ffi.GT_I64, B2, 81, 512, 40, 40, 320, 320,
           hist.ctypes.data, None, _ffi.GEMM_TF32X3, 0)
+# peer-memory all-reduce, world size 1 (the multi-GPU exchange is exercised by tools/p2p_reduce_probe.py)
+import ctypes as C
+handle = (C.c_ubyte * 64)(); ctx = C.c_int(-1)
+_ffi.call("zutis_p2p_create", 1, 0, 81 * 81, C.addressof(handle), C.addressof(ctx))
+_ffi.call("zutis_p2p_connect", ctx.value, C.addressof(handle))
+hh = torch.arange(81 * 81, device="cuda", dtype=torch.int64); oo = torch.empty_like(hh)
+for _ in range(3):
+    _ffi.call("zutis_allreduce_hist_p2p", ctx.value, hh.data_ptr(), hh.numel(), oo.data_ptr(), torch.cuda.current_stream().cuda_stream)
+torch.cuda.synchronize(); assert torch.equal(hh, oo)
+_ffi.call("zutis_p2p_destroy", ctx.value)
 scorer = zutis_b200.StreamingScorer(text, zutis_b200.RunningScore(81), (224, 224))
 scorer.submit(tokens, gt); scorer.submit(tokens, gt); scorer.get_scores()
 ops.upsample_bilinear(lo2, (50, 60))

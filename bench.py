@@ -526,13 +526,15 @@ def strong_scaling(args, cfg, device, rank, world, dist, peer=None):
     use_peer = peer is not None and world > 1 and Q * Q <= peer.max_elements
 
     def one(i):
+        if use_peer:                                         # the merge of the int32 partial rides in the all-reduce kernel
+            runner.step(i)
+            peer.merge_all_reduce(runner.meter._hist, runner.meter._partial, reduced)
+            runner.meter._pending = 0
+            return
         runner.step(i, merge_now=True)
-        if use_peer:
-            peer.all_reduce(runner.meter._hist, out=reduced)
-        else:
-            reduced.copy_(runner.meter._hist)
-            if world > 1:
-                dist.all_reduce(reduced, op=dist.ReduceOp.SUM)
+        reduced.copy_(runner.meter._hist)
+        if world > 1:
+            dist.all_reduce(reduced, op=dist.ReduceOp.SUM)
 
     for i in range(4):
         one(i)
@@ -583,9 +585,10 @@ def strong_scaling(args, cfg, device, rank, world, dist, peer=None):
     ms = sorted(passes)[1]
     # the N-rank reduced matrix of ONE pass over input set 0 must equal rank 0's single-GPU matrix over the same images
     runner.meter.reset()
-    runner.step(0, merge_now=True)
+    runner.step(0, merge_now=not use_peer)
     if use_peer:
-        peer.all_reduce(runner.meter._hist, out=reduced)
+        peer.merge_all_reduce(runner.meter._hist, runner.meter._partial, reduced)
+        runner.meter._pending = 0
     else:
         reduced.copy_(runner.meter._hist)
         if world > 1:
@@ -602,7 +605,8 @@ def strong_scaling(args, cfg, device, rank, world, dist, peer=None):
             "reduced_matrix_equals_single_gpu": equal,
             "allreduce": ("zutis_allreduce_hist_p2p (own kernel over NVLink peer memory)" if use_peer else
                           ("NCCL via torch.distributed" if world > 1 else "none (one GPU)")),
-            "step": "contraction + decode_score + hist_merge + all_reduce(int64 Q x Q), one graph replay per step, max over ranks"}
+            "step": ("contraction + decode_score + [hist_merge + all_reduce(int64 Q x Q) in one kernel]" if use_peer else
+                     "contraction + decode_score + hist_merge + all_reduce(int64 Q x Q)") + ", one graph replay per step, max over ranks"}
 
 
 def allreduce_timing(device, world, dist, peer=None):

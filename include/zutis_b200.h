@@ -159,6 +159,9 @@ ZUTIS_API int zutis_allreduce_hist(long long* hist_i64, long n2, void* nccl_comm
 ZUTIS_API int zutis_p2p_create(int world, int rank, long max_n2, unsigned char* ipc_handle_out, int* ctx_out);
 ZUTIS_API int zutis_p2p_connect(int ctx, const unsigned char* handles);
 ZUTIS_API int zutis_allreduce_hist_p2p(int ctx, const long long* hist, long n2, long long* out, void* stream);
+/* ... with this rank's pending int32 partial folded in first (hist += partial; partial = 0), i.e. zutis_hist_merge and the
+ * all-reduce in one launch; out must not be hist. */
+ZUTIS_API int zutis_merge_allreduce_hist_p2p(int ctx, long long* hist, int32_t* partial, long n2, long long* out, void* stream);
 ZUTIS_API int zutis_p2p_destroy(int ctx);
 
 /* ---------------------------------------------------------------------------------------------

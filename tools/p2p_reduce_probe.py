@@ -21,6 +21,23 @@ for Q in (81, 21, 128):
     out = torch.empty_like(mine)
     red.all_reduce(mine, out=out)
     ok &= bool(torch.equal(out, want))
+# merge + all-reduce in one launch: counts += partial; partial = 0; out = sum over ranks
+cnt = torch.randint(0, 1 << 40, (81 * 81,), device=dev, dtype=torch.int64)
+part = torch.randint(0, 1 << 20, (81 * 81,), device=dev, dtype=torch.int32)
+want = cnt + part.long(); want_local = want.clone(); dist.all_reduce(want)
+fused_out = torch.empty_like(cnt)
+red.merge_all_reduce(cnt, part, fused_out)
+ok &= bool(torch.equal(fused_out, want)) and bool(torch.equal(cnt, want_local)) and int(part.abs().sum()) == 0
+# RunningScore.all_reduce(peer=...) with counts still pending in the int32 partial, against the torch.distributed route
+import zutis_b200
+g2 = torch.Generator().manual_seed(7 + rank)
+gt = torch.randint(0, 81, (2, 64, 64), generator=g2).cuda(); pr = torch.randint(0, 81, (2, 64, 64), generator=g2).cuda()
+m1, m2 = zutis_b200.RunningScore(81, device=dev), zutis_b200.RunningScore(81, device=dev)
+m1.update(gt, pr); m2.update(gt, pr)
+m1.all_reduce(peer=red); m2.all_reduce()
+ok &= bool(torch.equal(m1.counts(), m2.counts())) and int(m1.counts().sum()) == world * 2 * 64 * 64
+m1.all_reduce(peer=red)                                   # nothing pending: the plain in-place call
+ok &= int(m1.counts().sum()) == world * world * 2 * 64 * 64
 # latency, back to back
 Q = 81
 buf = torch.ones(Q * Q, device=dev, dtype=torch.int64); out = torch.empty_like(buf)

@@ -57,6 +57,7 @@ SIGNATURES = {
     "zutis_p2p_create": (_i, [_i, _i, _l, _vp, _vp]),
     "zutis_p2p_connect": (_i, [_i, _vp]),
     "zutis_allreduce_hist_p2p": (_i, [_i, _vp, _l, _vp, _vp]),
+    "zutis_merge_allreduce_hist_p2p": (_i, [_i, _vp, _vp, _l, _vp, _vp]),
     "zutis_p2p_destroy": (_i, [_i]),
     "zutis_upsample_bilinear": (_i, [_vp, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "zutis_decode_threshold": (_i, [_vp, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),

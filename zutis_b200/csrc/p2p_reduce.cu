@@ -65,15 +65,23 @@ __device__ __forceinline__ void flag_wait(char* const* peers, size_t data_bytes,
 
 // counters: [0] epoch of the last finished call, [1] CTAs that have staged (monotonic), [2] CTAs that have summed (monotonic)
 __global__ void __launch_bounds__(1024) p2p_allreduce_kernel(char* const* __restrict__ peers, size_t data_bytes, int rank, int world,
-                                                             const long long* __restrict__ hist, long n2, long long* __restrict__ out,
-                                                             unsigned* counters) {
+                                                             long long* __restrict__ hist, int* __restrict__ partial, long n2,
+                                                             long long* __restrict__ out, unsigned* counters) {
     const unsigned epoch = *reinterpret_cast<volatile unsigned*>(counters) + 1u;      // advanced by the last CTA, at the very end
     const long stride = (long)gridDim.x * blockDim.x, first = (long)blockIdx.x * blockDim.x + threadIdx.x;
     // Two staging buffers, taken in turns: a peer that has arrived for call e has finished reading call e-1, so when this
     // rank restages buffer e % 2 at call e, every peer is done with what call e-2 left there -- no second handshake.
     const size_t half = data_bytes / 2, mine_off = (epoch & 1u) ? half : 0;
     long long* staging = reinterpret_cast<long long*>(peers[rank] + mine_off);
-    for (long i = first; i < n2; i += stride) staging[i] = hist[i];
+    if (partial) {
+        // the "+=" of running_score.py:20 for the launches since the last merge, folded into the staging pass
+        for (long i = first; i < n2; i += stride) {
+            const long long v = hist[i] + (long long)partial[i];
+            hist[i] = v; partial[i] = 0; staging[i] = v;
+        }
+    } else {
+        for (long i = first; i < n2; i += stride) staging[i] = hist[i];
+    }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) atomicAdd(counters + 1, 1u);
@@ -148,14 +156,23 @@ extern "C" int zutis_p2p_connect(int ctx, const unsigned char* handles) {
     return ZUTIS_OK;
 }
 
+extern "C" int zutis_merge_allreduce_hist_p2p(int ctx, long long* hist, int32_t* partial, long n2, long long* out, void* stream);
+
 // out[i] = sum over ranks of hist_r[i], i < n2; hist and out are this rank's device buffers (they may be the same buffer:
 // the matrix is staged before it is summed).  Enqueued on `stream`; graph-capturable.
 extern "C" int zutis_allreduce_hist_p2p(int ctx, const long long* hist, long n2, long long* out, void* stream) {
+    return zutis_merge_allreduce_hist_p2p(ctx, const_cast<long long*>(hist), nullptr, n2, out, stream);
+}
+
+// The same with the pending int32 partial of this rank folded in first (hist += partial; partial = 0), i.e.
+// zutis_hist_merge + zutis_allreduce_hist_p2p in one launch.  out must not be hist here.
+extern "C" int zutis_merge_allreduce_hist_p2p(int ctx, long long* hist, int32_t* partial, long n2, long long* out, void* stream) {
     ZUTIS_REQUIRE(ctx >= 0 && ctx < 64 && g_ctx[ctx], "zutis_allreduce_hist_p2p: bad context");
     P2PContext* c = g_ctx[ctx];
     ZUTIS_REQUIRE(c->connected, "zutis_allreduce_hist_p2p: zutis_p2p_connect has not been called");
     ZUTIS_REQUIRE(hist && out && n2 > 0 && (size_t)n2 * 8 <= c->data_bytes / 2, "zutis_allreduce_hist_p2p: n2=%ld does not fit the context", n2);
-    p2p_allreduce_kernel<<<kCtas, 1024, 0, (cudaStream_t)stream>>>(c->d_peers, c->data_bytes, c->rank, c->world, hist, n2, out, c->d_epoch);
+    ZUTIS_REQUIRE(!partial || out != hist, "zutis_merge_allreduce_hist_p2p: out must not alias hist");
+    p2p_allreduce_kernel<<<kCtas, 1024, 0, (cudaStream_t)stream>>>(c->d_peers, c->data_bytes, c->rank, c->world, hist, partial, n2, out, c->d_epoch);
     return check_launch("p2p_allreduce_kernel");
 }
 

@@ -86,6 +86,15 @@ class PeerReducer:
                          torch.cuda.current_stream(self.device).cuda_stream)
         return out
 
+    def merge_all_reduce(self, counts: torch.Tensor, partial: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """counts += partial; partial = 0; out = sum over ranks of counts -- the merge kernel and the all-reduce in one launch."""
+        if counts.numel() > self.max_elements or out.data_ptr() == counts.data_ptr():
+            raise ValueError("PeerReducer.merge_all_reduce: matrix too large for this reducer, or out aliases counts")
+        with torch.cuda.device(self.device):
+            self._F.call("zutis_merge_allreduce_hist_p2p", self.ctx, counts.data_ptr(), partial.data_ptr(), counts.numel(), out.data_ptr(),
+                         torch.cuda.current_stream(self.device).cuda_stream)
+        return out
+
     def close(self) -> None:
         if getattr(self, "ctx", -1) >= 0:
             with torch.cuda.device(self.device):

@@ -113,10 +113,17 @@ class RunningScore(object):
         """Sum the per-GPU matrices (one int64 all-reduce of n^2 counts): over the torch.distributed process group; for
         hosts that own a raw NCCL communicator over ``nccl_comm`` (the ncclComm_t as an integer) through the C ABI; or over
         NVLink peer memory with a ``distributed.PeerReducer`` (one node, small matrices: a third of NCCL's latency)."""
-        self._merge()
         if peer is not None and self._hist.numel() <= peer.max_elements:
-            peer.all_reduce(self._hist)
+            if self._pending:                                 # merge and all-reduce in one launch
+                if getattr(self, "_reduced", None) is None:
+                    self._reduced = torch.empty_like(self._hist)
+                peer.merge_all_reduce(self._hist, self._partial, self._reduced)
+                self._hist, self._reduced = self._reduced, self._hist
+                self._pending = 0
+            else:
+                peer.all_reduce(self._hist)
             return
+        self._merge()
         if nccl_comm is not None:
             with torch.cuda.device(self.device):
                 ops.F.call("zutis_allreduce_hist", self._hist.data_ptr(), self._hist.numel(), nccl_comm,

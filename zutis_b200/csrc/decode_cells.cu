@@ -438,17 +438,20 @@ __global__ void __launch_bounds__(kCellWarpsMax * 32, 1) decode_cells_kernel(con
         const int ys = (int)lds_u32(a_ystart + (uint32_t)cy * 4u), ye = (int)lds_u32(a_ystart + (uint32_t)cy * 4u + 4u);
         const unsigned img_px = (unsigned)b * (unsigned)(p.H * p.W);
         const GT* gt_img = gt_base + (size_t)b * p.gt_sb;
-        // ---- all full 8x8 cells of the run at once: lane = (cell, column), 8 rows per lane.  The four lists are walked
-        // together (a lane past the end of its list reads the -inf record), so the per-run work is shared by the cells.
+        // ---- the bottom-right 8x8 block of every cell of the run at once (the whole cell at 8x up-sampling; the clamped
+        // border cells are taller / wider and leave an L-shaped rest to the per-cell path below): lane = (cell, column),
+        // 8 rows per lane.  The four lists are walked together (a lane past the end of its list reads the -inf record),
+        // so the per-run work is shared by the cells.
         unsigned fast_mask;
         {
             const int xs_m = (int)lds_u32(a_xstart + (uint32_t)min(cx_begin + cell, p.w) * 4u);
             const int xe_m = (int)lds_u32(a_xstart + (uint32_t)min(cx_begin + cell + 1, p.w) * 4u);
-            const bool fast_m = (ye - ys == 8) && cell < cells_here && (xe_m - xs_m == 8) && n <= cap;
+            const bool fast_m = (ye - ys >= 8) && cell < cells_here && (xe_m - xs_m >= 8) && n <= cap;
             fast_mask = __ballot_sync(kFull, fast_m);
             if (fast_mask) {
-                const int X = min(xs_m + slice, p.W - 1);
-                const unsigned px0 = (unsigned)ys * (unsigned)p.W + (unsigned)X;                 // row ys of this lane's column
+                const int yf = ye - 8;                                                             // first row of the block
+                const int X = min(max(xe_m - 8, 0) + slice, p.W - 1);
+                const unsigned px0 = (unsigned)yf * (unsigned)p.W + (unsigned)X;                 // row yf of this lane's column
                 GT g[8];
                 if (p.hist) {
                     const GT* gp = gt_img + px0;
@@ -462,7 +465,7 @@ __global__ void __launch_bounds__(kCellWarpsMax * 32, 1) decode_cells_kernel(con
                 unsigned long long LY0[4], LY1[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float4 t = lds128(a_lyp + (uint32_t)(ys + 2 * q) * 16u);
+                    const float4 t = lds128(a_lyp + (uint32_t)(yf + 2 * q) * 16u);
                     LY0[q] = pack2(t.x, t.y); LY1[q] = pack2(t.z, t.w);
                 }
                 float best[8];
@@ -520,10 +523,13 @@ __global__ void __launch_bounds__(kCellWarpsMax * 32, 1) decode_cells_kernel(con
         // ---- the other cells of the run, one at a time: lane = pixel pair of an 8x8 tile of the cell
 #pragma unroll 1
         for (int ci = 0; ci < cells_here; ++ci) {
-            if (fast_mask & (1u << (ci * kSlices))) continue;
             const int cx = cx_begin + ci;
             const int nc = __shfl_sync(kFull, n, ci * kSlices);
             const int xs = (int)lds_u32(a_xstart + (uint32_t)cx * 4u), xe = (int)lds_u32(a_xstart + (uint32_t)cx * 4u + 4u);
+            // the block [yb, ye) x [xb, xe) is done already (empty if this cell had none); an 8x8 cell is finished
+            const bool had_block = (fast_mask & (1u << (ci * kSlices))) != 0;
+            if (had_block && ye - ys == 8 && xe - xs == 8) continue;
+            const int yb = had_block ? ye - 8 : ye, xb = had_block ? xe - 8 : xe;
             const uint32_t val = val_base + (uint32_t)(ci * (cap + 1)) * 16u;
             const uint32_t ids = id_base + (uint32_t)(ci * (cap + 1)) * 2u;
             const bool vec = p.pair_ok && ((xs & 1) == 0);
@@ -533,8 +539,10 @@ __global__ void __launch_bounds__(kCellWarpsMax * 32, 1) decode_cells_kernel(con
                 const bool oky = Y < ye;
                 const float2 ly = lds_f2(a_ly + (uint32_t)min(Y, p.H - 1) * 8u);
                 for (int tx = xs; tx < xe; tx += 8) {
+                    if (ty >= yb && tx >= xb) continue;                                      // tile inside the finished block
                     const int X0 = tx + c2;
-                    const bool ok0 = oky && X0 < xe, ok1 = oky && X0 + 1 < xe;
+                    const bool in_rows = Y >= yb;
+                    const bool ok0 = oky && X0 < xe && !(in_rows && X0 >= xb), ok1 = oky && X0 + 1 < xe && !(in_rows && X0 + 1 >= xb);
                     // on the vector path a pair is stored / loaded only as a whole; the odd last column of a cell goes scalar
                     const bool vec_here = vec && (ok0 == ok1);
                     const unsigned px = (unsigned)Y * (unsigned)p.W + (unsigned)X0;

@@ -88,6 +88,22 @@ void narrow_labels(const void* src, int src_code, void* dst, int dst_code, size_
     }
 }
 
+int usable_cpus();
+
+// Host threads that narrow the labels of one call.  ZUTIS_HOST_THREADS overrides; otherwise the CPUs this process may use
+// are shared out among the ranks of the node (LOCAL_WORLD_SIZE, set by torchrun), one is left to the enqueueing thread,
+// and more than four do not help (the narrowing of a chunk only has to keep ahead of the 8x larger token copy).
+int narrowing_threads() {
+    if (const char* e = getenv("ZUTIS_HOST_THREADS")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 64) return v;
+    }
+    int ranks = 1;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e) > 0 ? atoi(e) : 1;
+    int n = usable_cpus() / ranks - 1;
+    return n < 1 ? 1 : (n > 4 ? 4 : n);
+}
+
 int usable_cpus() {
     cpu_set_t set;
     CPU_ZERO(&set);
@@ -176,7 +192,7 @@ extern "C" int zutis_semantic_eval_host(const float* text, const float* tokens, 
     if (narrow) {
         for (auto& a : narrowed) a.store(0, std::memory_order_relaxed);
         const size_t total = (size_t)B * HW;
-        n_workers = total * src_gt_bytes < (4u << 20) ? 0 : (usable_cpus() >= 8 ? 4 : (usable_cpus() >= 3 ? 2 : 1));
+        n_workers = total * src_gt_bytes < (4u << 20) ? 0 : narrowing_threads();
         void* staging = c.h_gt;
         auto work = [=, &narrowed](int t, int T) {
             for (long k = 0; k < n_chunks; ++k) {

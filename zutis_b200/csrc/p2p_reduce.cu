@@ -104,6 +104,15 @@ __global__ void __launch_bounds__(1024) p2p_allreduce_kernel(char* const* __rest
         *reinterpret_cast<volatile unsigned*>(counters) = epoch;      // last CTA of this call
 }
 
+// frees what a context owns (not the peers' mappings) and the context itself
+void release(P2PContext* c) {
+    if (c->local) cudaFree(c->local);
+    if (c->d_peers) cudaFree(c->d_peers);
+    if (c->d_epoch) cudaFree(c->d_epoch);
+    (void)cudaGetLastError();
+    delete c;
+}
+
 }  // namespace
 
 // Step 1 of 2: allocate this rank's block and export its IPC handle (64 bytes) for the peers.
@@ -123,17 +132,17 @@ extern "C" int zutis_p2p_create(int world, int rank, long max_n2, unsigned char*
         cudaMalloc(&c->d_peers, kMaxWorld * sizeof(char*)) != cudaSuccess || cudaMalloc(&c->d_epoch, 4 * sizeof(unsigned)) != cudaSuccess ||
         cudaMemset(c->d_epoch, 0, 4 * sizeof(unsigned)) != cudaSuccess) {
         const int rc = check_cuda(cudaGetLastError(), "zutis_p2p_create allocation");
-        delete c;
+        release(c);
         return rc != ZUTIS_OK ? rc : fail(ZUTIS_ERR_CUDA, "zutis_p2p_create: allocation failed");
     }
     cudaIpcMemHandle_t h;
     st = check_cuda(cudaIpcGetMemHandle(&h, c->local), "cudaIpcGetMemHandle");
-    if (st != ZUTIS_OK) { delete c; return st; }
+    if (st != ZUTIS_OK) { release(c); return st; }
     memcpy(ipc_handle_out, &h, 64);
     std::lock_guard<std::mutex> lk(g_mu);
     for (int i = 0; i < 64; ++i)
         if (!g_ctx[i]) { g_ctx[i] = c; *ctx_out = i; return ZUTIS_OK; }
-    delete c;
+    release(c);
     return fail(ZUTIS_ERR_UNSUPPORTED, "zutis_p2p_create: too many contexts");
 }
 
@@ -183,12 +192,10 @@ extern "C" int zutis_p2p_destroy(int ctx) {
     cudaDeviceSynchronize();
     for (int r = 0; r < c->world; ++r)
         if (r != c->rank && c->peers[r]) cudaIpcCloseMemHandle(c->peers[r]);
-    cudaFree(c->local); cudaFree(c->d_peers); cudaFree(c->d_epoch);
-    (void)cudaGetLastError();
     {
         std::lock_guard<std::mutex> lk(g_mu);
         g_ctx[ctx] = nullptr;
     }
-    delete c;
+    release(c);
     return ZUTIS_OK;
 }
